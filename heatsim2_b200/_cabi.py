@@ -1,0 +1,78 @@
+"""ctypes binding of libhs2b200.so (include/hs2_b200.h).
+
+Loading is explicit and loud: if the CUDA library has not been built, or fails
+to load, an ImportError/RuntimeError is raised - there is no fallback path.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhs2b200.so")
+
+HS2_COEF_STRIDE = 8
+HS2_LU_STRIDE = 4
+ABI_VERSION = 1
+
+c_void_p = ctypes.c_void_p
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class PlanDesc(ctypes.Structure):
+    _fields_ = [
+        ("nz", ctypes.c_int64), ("ny", ctypes.c_int64), ("nx", ctypes.c_int64),
+        ("n_classes", ctypes.c_int32), ("class_id_bytes", ctypes.c_int32),
+        ("d_class_id", c_void_p), ("d_class_coef", c_void_p),
+        ("d_line_id", c_void_p * 3), ("d_line_lu", c_void_p * 3),
+        ("n_unique", ctypes.c_int32 * 3), ("device", ctypes.c_int32),
+    ]
+
+
+class Source(ctypes.Structure):
+    _fields_ = [("d_vol_elements", c_void_p), ("h_value", c_double_p), ("d_dense", c_void_p)]
+
+
+class Hs2Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); the list is also what tests check against the header
+PROTOTYPES = {
+    "hs2_abi_version": (ctypes.c_int, []),
+    "hs2_last_error": (ctypes.c_char_p, []),
+    "hs2_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.POINTER(c_void_p)]),
+    "hs2_plan_destroy": (ctypes.c_int, [c_void_p]),
+    "hs2_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
+    "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
+    "hs2_sweep_y": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "hs2_sweep_z": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hs2_tridiag_scratch_bytes": (ctypes.c_int64, [ctypes.c_int64]),
+    "hs2_tridiag_lu": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hs2_tridiag_solve": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    """The loaded library (cached).  Raises ImportError when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "heatsim2_b200: %s is missing - build it with "
+                "`python heatsim2_b200/build.py` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.hs2_abi_version() != ABI_VERSION:
+            raise ImportError("heatsim2_b200: ABI version mismatch (%d != %d); rebuild the library"
+                              % (L.hs2_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Hs2Error("hs2_b200 error %d: %s" % (rc, lib().hs2_last_error().decode("utf-8", "replace")))

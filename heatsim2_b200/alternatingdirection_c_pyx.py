@@ -1,0 +1,254 @@
+"""ADI stage bookkeeping and the time-step entry point.
+
+Host-side mirror of the reference's ``heatsim2/alternatingdirection_c_pyx.pyx``
+(+ the C container ``alternatingdirection_c.c``) with the same public names:
+
+    adi_params :75      pyadi_step :120     adi_setup :418
+    adi_expressions :475                    add_equation_to_adi_matrices :447
+    run_adi_steps :287
+
+What changed underneath: the reference stores, per stage, an ``n x 3``
+tridiagonal, COO/CSR matrices B, C0, C1 and a vector D (1.5 kB per cell) and
+each step does 3 x {SpMV + one length-n Thomas chain} on one CPU thread.  Here a
+stage is described by per-equation-class coefficients (a few dozen rows of 8
+doubles) plus per-unique-line Thomas factors; ``run_adi_steps`` hands the field
+to the CUDA library (``_cabi`` -> libhs2b200.so).  The matrices the reference
+exposes as attributes (``Amat``, ``Bmat``, ``Cmats``, ``Dvec``, ``Lmat``,
+``Umat``) can still be materialised on the host for inspection of small grids.
+"""
+import numpy as np
+
+from . import expression
+from .expression import crank_subst_in_groups, eliminate_groups
+
+# sweep order of the three Douglas stages: (axis name, permuteorder)
+_STAGES = (("x", (0, 1, 2)), ("y", (2, 0, 1)), ("z", (1, 2, 0)))
+
+
+class adi_params(object):
+    """Problem-wide parameters shared by the stages (reference :75-85).
+    Unknown keyword -> ValueError, as in the reference."""
+    shape = None
+    volume_array = None
+    plan = None          # heatsim2_b200.plan.AdiPlan, attached by setup()
+
+    def __init__(self, **kwargs):
+        for key in kwargs:
+            if not hasattr(self, key):
+                raise ValueError("Unknown parameter %s (must add to class definition)" % key)
+            setattr(self, key, kwargs[key])
+
+
+class pyadi_step(object):
+    """One ADI stage (reference :120-284).  Keeps the reference's descriptive
+    attributes; the numerical content lives in ``ADI_params.plan``."""
+
+    def __init__(self, ADI_params, permuteorder, stepnum):
+        self.ADI_params = ADI_params
+        self.stepnum = stepnum
+        self.permuteorder = tuple(permuteorder)
+        self.permutedshape = [ADI_params.shape[a] for a in permuteorder]
+        self.invpermuteorder = tuple(int(a) for a in np.argsort(permuteorder))
+
+    def finalize(self):
+        """The reference converts COO->CSR and LU-factors here (:212-282);
+        the plan is complete as soon as setup() returns, so nothing to do."""
+        return None
+
+    # --- host-side materialisation of the reference's matrices (inspection /
+    #     tests on small grids only; never used by run_adi_steps) -------------
+    def _mats(self):
+        plan = self.ADI_params.plan
+        if plan is None:
+            raise RuntimeError("stage has no plan: call setup() first")
+        return plan.reference_matrices(self.stepnum)
+
+    @property
+    def Amat(self):
+        return self._mats()["A"]
+
+    @property
+    def Bmat(self):
+        return self._mats()["B"]
+
+    @property
+    def Cmats(self):
+        return self._mats()["C"]
+
+    @property
+    def Dvec(self):
+        return self._mats()["D"]
+
+    @property
+    def Lmat(self):
+        from . import tridiag
+        return tridiag.tridiaglu_host(self.Amat)[0]
+
+    @property
+    def Umat(self):
+        from . import tridiag
+        return tridiag.tridiaglu_host(self.Amat)[1]
+
+
+def adi_setup(shape, volume_array):
+    """Three stages, implicit in x, then y, then z (Douglas eq. 3.1a-c;
+    reference :418-445)."""
+    ADI_params = adi_params(shape=tuple(int(s) for s in shape), volume_array=volume_array)
+    ADI_steps = [pyadi_step(ADI_params, perm, s) for s, (_, perm) in enumerate(_STAGES)]
+    return (ADI_params, ADI_steps)
+
+
+def adi_expressions(spatial_expression, time_expression, unaligned_anisotropic=False):
+    """Stage equations from one cell's heat balance (reference :475-572).
+
+    Stage s time-averages (Crank-Nicolson) the flux groups of sweep directions
+    0..s and solves for ``T555p<s>``."""
+    if unaligned_anisotropic:
+        # The reference's 15-stage branch (:511-564) cannot run: adi_setup()
+        # creates 3 stages and add_equation_to_adi_matrices asserts equal
+        # counts (:452).  There is no behaviour to be compatible with.
+        raise NotImplementedError("unaligned anisotropic conduction is not supported "
+                                  "(the reference's 15-stage path is non-functional)")
+    spatial, times = [], []
+    cur = spatial_expression
+    for s, members in enumerate((("T556", "T555", "T554"), ("T565", "T555", "T545"), ("T655", "T555", "T455"))):
+        cur = crank_subst_in_groups(cur, members, s)
+        spatial.append(cur)
+        times.append(expression.subst(time_expression, "T555p", "T555p%d" % s))
+    spatial[-1] = spatial[-1].fullreduce()
+    # tensor conductivities not aligned with the grid leave cross-derivative groups behind
+    assert expression.no_groups(spatial[-1])
+    return (tuple(spatial), tuple(times))
+
+
+def stage_dicts(spatial_expressions, time_expressions):
+    """``{variable: coefficient}`` of every stage (what the reference caches in
+    ``aetam_cache``, :454-465)."""
+    return [eliminate_groups(sp + tm).dictform() for sp, tm in zip(spatial_expressions, time_expressions)]
+
+
+_OFFS = {"4": -1, "5": 0, "6": 1}
+
+
+def parse_stage_dict(eqdict, stepnum):
+    """Sort one stage dictionary into matrix entries by the rules of the
+    reference's C ``add_equation`` (alternatingdirection_c.c:102-199).
+
+    Returns ``(A, B, C, D)``: ``A`` maps the offset along the sweep axis to the
+    tridiagonal entry (sign flipped, :147); ``B`` and ``C[sol]`` map a
+    ``(dz,dy,dx)`` offset to the summed coefficient; ``D`` is the source weight."""
+    sweep_axis = _STAGES[stepnum][1][2]            # 2 (x), 1 (y), 0 (z) in (z,y,x) digit order
+    A, B, C, D = {}, {}, {}, 0.0
+    for name, value in eqdict.items():
+        if name == "volumetric_source":
+            D = value
+        elif name == "":
+            if value != 0.0:
+                raise ValueError("equation has a constant term %g; boundaries must be homogeneous" % value)
+        else:
+            if name[0] != "T" or len(name) < 4 or any(ch not in _OFFS for ch in name[1:4]):
+                raise ValueError("unexpected variable %r in a stage equation" % name)
+            off = tuple(_OFFS[ch] for ch in name[1:4])
+            tshift = name[4:5]
+            sol = int(name[5:]) if tshift == "p" and len(name) > 5 else 0
+            if tshift == "p" and sol == stepnum:
+                if any(off[a] != 0 for a in range(3) if a != sweep_axis):
+                    raise ValueError("implicit variable %r is not on the sweep axis of stage %d" % (name, stepnum))
+                A[off[sweep_axis]] = -value
+            elif tshift in ("m", ""):
+                B[off] = B.get(off, 0.0) + value
+            elif tshift == "p":
+                if sol > stepnum:
+                    raise ValueError("stage %d refers to later stage %d" % (stepnum, sol))
+                C.setdefault(sol, {})
+                C[sol][off] = C[sol].get(off, 0.0) + value
+            else:
+                raise ValueError("unexpected time suffix in %r" % name)
+    return A, B, C, D
+
+
+def class_coefficients(eqdicts, rtol=1e-9):
+    """Reduce the three stage dictionaries of one equation class to
+    ``(M, (gx-,gx+,gy-,gy+,gz-,gz+), D)`` and verify that the stages have the
+    conservative 7-point Douglas structure the kernels implement."""
+    parsed = [parse_stage_dict(d, s) for s, d in enumerate(eqdicts)]
+    g = []
+    M = None
+    for s in range(3):
+        A = parsed[s][0]
+        lo, hi, dg = -2.0 * A.get(-1, 0.0), -2.0 * A.get(1, 0.0), A.get(0, 0.0)
+        g += [lo, hi]
+        Ms = dg - 0.5 * (lo + hi)
+        M = Ms if M is None else M
+        scale = abs(dg) + abs(lo) + abs(hi)
+        if abs(Ms - M) > rtol * scale:
+            raise NotImplementedError("stage diagonals disagree on the capacity term (%g vs %g)" % (Ms, M))
+    D = parsed[0][3]
+    gx, gy, gz = (g[0], g[1]), (g[2], g[3]), (g[4], g[5])
+    sx, sy, sz = sum(gx), sum(gy), sum(gz)
+    scale = abs(M) + abs(sx) + abs(sy) + abs(sz)
+
+    def offs(axis, val):
+        o = [0, 0, 0]
+        o[axis] = val
+        return tuple(o)
+
+    def stencil(cx, cy, cz, centre):
+        st = {(0, 0, 0): centre}
+        for (axis, gg, c) in ((2, gx, cx), (1, gy, cy), (0, gz, cz)):
+            for sgn, gv in zip((-1, 1), gg):
+                if c * gv != 0.0:
+                    st[offs(axis, sgn)] = c * gv
+        return st
+
+    expect = [
+        (stencil(.5, 1, 1, M - .5 * sx - sy - sz), {}),
+        (stencil(.5, .5, 1, M - .5 * sx - .5 * sy - sz), {0: stencil(.5, 0, 0, -.5 * sx)}),
+        (stencil(.5, .5, .5, M - .5 * (sx + sy + sz)), {0: stencil(.5, 0, 0, -.5 * sx), 1: stencil(0, .5, 0, -.5 * sy)}),
+    ]
+
+    def same(got, want):
+        for key in set(got) | set(want):
+            if abs(got.get(key, 0.0) - want.get(key, 0.0)) > rtol * scale:
+                return False
+        return True
+
+    for s in range(3):
+        _, B, C, Ds = parsed[s]
+        ok = same(B, expect[s][0]) and all(same(C.get(c, {}), expect[s][1].get(c, {})) for c in set(C) | set(expect[s][1]))
+        if not ok or abs(Ds - D) > rtol * max(abs(D), 1.0):
+            raise NotImplementedError(
+                "stage %d of an equation class is not of the conservative 7-point Douglas form "
+                "supported by the CUDA kernels: B=%r C=%r" % (s, B, C))
+    return M, tuple(g), D
+
+
+def add_equation_to_adi_matrices(ADI_params, ADI_steps, k, j, i, key_params, aetam_cache,
+                                 spatial_expressions, time_expressions):
+    """Reference signature (:447-472).  The vectorised setup() never calls this
+    per cell; it is kept for code that assembles cell by cell: the equation is
+    recorded in the plan builder attached to ``ADI_params``."""
+    assert len(ADI_steps) == len(spatial_expressions)
+    try:
+        eqdicts = aetam_cache[key_params]
+    except KeyError:
+        eqdicts = stage_dicts(spatial_expressions, time_expressions)
+        aetam_cache[key_params] = eqdicts
+    builder = getattr(ADI_params, "_cell_builder", None)
+    if builder is None:
+        from .plan import CellwiseBuilder
+        builder = ADI_params._cell_builder = CellwiseBuilder(ADI_params.shape)
+    builder.add(k, j, i, key_params, eqdicts)
+
+
+def run_adi_steps(ADI_params, ADI_steps, t, dt, Tarray, volumetric_elements, volumetric):
+    """Advance ``Tarray`` (indexed [z,y,x], float64) by one ADI time step.
+
+    Same call as the reference (:287-416).  ``Tarray`` may be a numpy array -
+    it is copied to the device, stepped, and a new numpy array is returned,
+    like the reference - or a CUDA ``torch.Tensor``, in which case the result
+    is a new CUDA tensor and nothing crosses PCIe."""
+    plan = ADI_params.plan
+    if plan is None:
+        raise RuntimeError("ADI_params carries no plan; it must come from heatsim2_b200.setup()")
+    return plan.run_step(t, dt, Tarray, volumetric_elements, volumetric)

@@ -1,0 +1,86 @@
+// cabi.cu - extern "C" surface declared in include/hs2_b200.h.
+#include <stdarg.h>
+#include <new>
+
+#include "hs2_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void hs2_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+int hs2_abi_version(void) { return HS2_ABI_VERSION; }
+
+const char *hs2_last_error(void) { return g_err; }
+
+int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
+  HS2_REQUIRE(desc && out, "hs2_plan_create: NULL argument");
+  *out = nullptr;
+  HS2_REQUIRE(desc->nz > 0 && desc->ny > 0 && desc->nx > 0, "hs2_plan_create: empty grid %lld x %lld x %lld",
+              (long long)desc->nz, (long long)desc->ny, (long long)desc->nx);
+  HS2_REQUIRE(desc->class_id_bytes == 1 || desc->class_id_bytes == 2, "hs2_plan_create: class_id_bytes must be 1 or 2");
+  HS2_REQUIRE(desc->n_classes > 0 && desc->n_classes <= (desc->class_id_bytes == 1 ? 256 : 65536),
+              "hs2_plan_create: n_classes %d out of range for %d-byte ids", desc->n_classes, desc->class_id_bytes);
+  HS2_REQUIRE(desc->d_class_id && desc->d_class_coef, "hs2_plan_create: NULL class tables");
+  for (int a = 0; a < 3; ++a)
+    HS2_REQUIRE(desc->d_line_id[a] && desc->d_line_lu[a] && desc->n_unique[a] > 0,
+                "hs2_plan_create: missing line table for axis %d", a);
+  int ndev = 0;
+  HS2_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  HS2_REQUIRE(desc->device >= 0 && desc->device < ndev, "hs2_plan_create: device %d not present (%d visible)",
+              desc->device, ndev);
+  cudaDeviceProp prop;
+  HS2_CUDA_CHECK(cudaGetDeviceProperties(&prop, desc->device));
+  HS2_REQUIRE(prop.major == 10, "hs2_plan_create: built for sm_100a, device %d is sm_%d%d", desc->device, prop.major,
+              prop.minor);
+  hs2_plan *p = new (std::nothrow) hs2_plan;
+  if (!p) {
+    hs2_set_error("hs2_plan_create: out of host memory");
+    return HS2_E_NOMEM;
+  }
+  p->d = *desc;
+  p->n = desc->nz * desc->ny * desc->nx;
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = p;
+  return HS2_OK;
+}
+
+int hs2_plan_destroy(hs2_plan *plan) {
+  delete plan;
+  return HS2_OK;
+}
+
+int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src, const double *d_halo_lo,
+                const double *d_halo_hi, void *stream) {
+  HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
+  HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
+  return hs2_v1_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
+}
+
+int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream) {
+  HS2_REQUIRE(plan && d_work, "hs2_sweep_y: NULL argument");
+  return hs2_v1_sweep_y(plan, d_work, (cudaStream_t)stream);
+}
+
+int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, void *stream) {
+  HS2_REQUIRE(plan && d_T_in && d_T_out && d_work, "hs2_sweep_z: NULL argument");
+  return hs2_v1_sweep_z(plan, d_T_in, d_T_out, d_work, (cudaStream_t)stream);
+}
+
+int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const hs2_source *src,
+             const double *d_halo_lo, const double *d_halo_hi, void *stream) {
+  int rc = hs2_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, stream);
+  if (rc) return rc;
+  rc = hs2_sweep_y(plan, d_work, stream);
+  if (rc) return rc;
+  return hs2_sweep_z(plan, d_T_in, d_T_out, d_work, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Shared declarations of the hs2_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hs2_b200.h"
+
+struct hs2_plan {
+  hs2_plan_desc d;
+  int64_t n;           // nz*ny*nx
+  int sm_count;
+  int max_smem_optin;
+};
+
+void hs2_set_error(const char *fmt, ...);
+
+#define HS2_CUDA_CHECK(call)                                                   \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      hs2_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                    __FILE__, __LINE__);                                       \
+      return HS2_E_CUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+#define HS2_REQUIRE(cond, ...)                                                 \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      hs2_set_error(__VA_ARGS__);                                              \
+      return HS2_E_INVALID;                                                    \
+    }                                                                          \
+  } while (0)
+
+// kernels_v1.cu - global-memory reference-quality path (any size)
+int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src,
+                   const double *halo_lo, const double *halo_hi, cudaStream_t st);
+int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
+int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);

@@ -1,0 +1,452 @@
+"""AdiPlan - everything the CUDA kernels need for one problem, and the host
+logic that drives them.
+
+A plan is built by ``crank_nicolson.setup`` from
+  * ``class_id``   per-cell equation-class index (u8/u16 array [nz,ny,nx]),
+  * ``class_coef`` per-class ``(M, gx-,gx+,gy-,gy+,gz-,gz+, D)``,
+and derives, per sweep axis, the set of *unique tridiagonal lines* and their
+Thomas factors.  The reference keeps ``Amat/Lmat/Umat`` (9 doubles per cell per
+stage, heatsim2/tridiag.pyx:9-43); all BASELINE grids have a handful of unique
+lines per axis, so the factor tables here are a few kB and live in L1/L2.
+
+torch tensors are used as device buffers only; every kernel launch goes through
+the C ABI (``_cabi``).  Nothing here computes a time step on the CPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+# column order of class_coef rows kept on the host (un-scaled, as parsed)
+M_, GXM, GXP, GYM, GYP, GZM, GZP, D_ = range(8)
+
+_AXIS_G = ((GXM, GXP), (GYM, GYP), (GZM, GZP))     # axis 0=x, 1=y, 2=z
+
+
+def _line_view(a3, axis):
+    """View a [nz,ny,nx] tensor as [n_lines, L] rows for sweep axis 0=x,1=y,2=z
+    with the library's line numbering (x: k*ny+j, y: k*nx+i, z: j*nx+i)."""
+    nz, ny, nx = a3.shape
+    if axis == 0:
+        return a3.reshape(nz * ny, nx)
+    if axis == 1:
+        return a3.permute(0, 2, 1).reshape(nz * nx, ny)
+    return a3.permute(1, 2, 0).reshape(ny * nx, nz)
+
+
+def thomas_factors(lo, dg, hi):
+    """Thomas factorisation of a batch of tridiagonal lines [n_unique, L]:
+    returns [n_unique, L, 4] = {1/pivot, lo/pivot, hi/pivot, 0}
+    (same recurrence as heatsim2/tridiag.pyx:25-41, stored as reciprocals)."""
+    nu, L = dg.shape
+    out = np.zeros((nu, L, _cabi.HS2_LU_STRIDE))
+    cp_prev = np.zeros(nu)
+    for r in range(L):
+        piv = dg[:, r] - lo[:, r] * cp_prev
+        inv = 1.0 / piv
+        cp_prev = hi[:, r] * inv
+        out[:, r, 0] = inv
+        out[:, r, 1] = lo[:, r] * inv
+        out[:, r, 2] = cp_prev
+    return out
+
+
+class AdiPlan(object):
+    def __init__(self, shape, class_id, class_coef, dt, volume_array, volumetric_elements=None,
+                 materials=None):
+        self.shape = tuple(int(s) for s in shape)
+        nz, ny, nx = self.shape
+        self.n = nz * ny * nx
+        self.dt = dt
+        self.volume_array = volume_array
+        self.materials = materials
+        self.class_coef = np.ascontiguousarray(class_coef, dtype=np.float64)     # [nc, 8] un-scaled
+        self.n_classes = self.class_coef.shape[0]
+        if self.n_classes > 65536:
+            raise NotImplementedError("more than 65536 equation classes (%d)" % self.n_classes)
+        cid = class_id if isinstance(class_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(class_id))
+        want = torch.uint8 if self.n_classes <= 256 else torch.int16    # int16 carries u16 bit patterns
+        if cid.dtype != want:
+            cid = cid.to(torch.int64).to(want) if want == torch.uint8 else cid.to(torch.int32).to(torch.int16)
+        self.class_id = cid.reshape(self.shape).contiguous()
+        self._setup_vol_elements = volumetric_elements
+        self._check_closed()
+        self._build_lines()
+        self._dev = None
+        self._handle = None
+        self._bufs = {}
+        self._vol_dev = None
+        self._vol_key = None
+
+    # ------------------------------------------------------------ validation
+    def _check_closed(self):
+        """No conductance may point out of the domain.  The reference detects
+        this inside C add_equation and calls exit(1)
+        (alternatingdirection_c.c:160-163); here it is a ValueError."""
+        cid = self.class_id
+        faces = ((cid[0], GZM, "z-min"), (cid[-1], GZP, "z-max"),
+                 (cid[:, 0], GYM, "y-min"), (cid[:, -1], GYP, "y-max"),
+                 (cid[:, :, 0], GXM, "x-min"), (cid[:, :, -1], GXP, "x-max"))
+        for sl, col, name in faces:
+            ids = torch.unique(sl.to(torch.int32) & 0xFFFF).cpu().numpy()
+            if np.any(self.class_coef[ids, col] != 0.0):
+                raise ValueError("Equation exceeds bounds of domain on the %s face. "
+                                 "Are external boundaries set correctly?" % name)
+
+    # ------------------------------------------------------- unique line tables
+    def _build_lines(self):
+        cc = self.class_coef
+        M = cc[:, M_]
+        self.scaled_coef = np.zeros((self.n_classes, _cabi.HS2_COEF_STRIDE))
+        self.scaled_coef[:, 0:6] = cc[:, GXM:GZP + 1] / M[:, None]
+        self.scaled_coef[:, 6] = cc[:, D_] / M
+        self.scaled_coef[:, 7] = M
+        cid = self.class_id
+        cid_i = (cid.to(torch.int32) & 0xFFFF) if cid.dtype == torch.int16 else cid
+        self.line_id, self.line_lu, self.line_rows = [], [], []
+        for axis in range(3):
+            gm, gp = _AXIS_G[axis]
+            rows = np.stack([-0.5 * cc[:, gm] / M, 1.0 + 0.5 * (cc[:, gm] + cc[:, gp]) / M, -0.5 * cc[:, gp] / M], axis=1)
+            urows, sub_of_class = np.unique(rows, axis=0, return_inverse=True)
+            sub_of_class = sub_of_class.reshape(-1)
+            sub_lut = torch.from_numpy(sub_of_class.astype(np.int64)).to(cid.device)
+            lid, reps = _unique_lines(cid_i, sub_lut, axis, len(urows))
+            lo, dg, hi = (urows[:, c][reps] for c in range(3))
+            self.line_id.append(lid)                       # int32 tensor [n_lines]
+            self.line_rows.append((lo, dg, hi))            # numpy [n_unique, L] each
+            self.line_lu.append(thomas_factors(lo, dg, hi))
+
+    @property
+    def n_unique(self):
+        return tuple(int(t.shape[0]) for t in self.line_lu)
+
+    # ------------------------------------------------------------- device side
+    def ensure_device(self, device=None):
+        if self._handle is not None and (device is None or torch.device(device) == self._dev):
+            return
+        if not torch.cuda.is_available():
+            raise RuntimeError("heatsim2_b200 needs a CUDA device (B200, sm_100a); there is no CPU time-step path")
+        lib = _cabi.lib()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.release()
+        self._dev = dev
+        self.d_class_id = self.class_id.to(dev)
+        self.class_id = self.d_class_id            # keep a single copy
+        self.d_coef = torch.from_numpy(self.scaled_coef).to(dev)
+        self.d_line_id = [t.to(dev).contiguous() for t in self.line_id]
+        self.d_line_lu = [torch.from_numpy(t).to(dev).contiguous() for t in self.line_lu]
+        desc = _cabi.PlanDesc()
+        desc.nz, desc.ny, desc.nx = self.shape
+        desc.n_classes = self.n_classes
+        desc.class_id_bytes = self.d_class_id.element_size()
+        desc.d_class_id = self.d_class_id.data_ptr()
+        desc.d_class_coef = self.d_coef.data_ptr()
+        for a in range(3):
+            desc.d_line_id[a] = self.d_line_id[a].data_ptr()
+            desc.d_line_lu[a] = self.d_line_lu[a].data_ptr()
+            desc.n_unique[a] = self.d_line_lu[a].shape[0]
+        desc.device = dev.index
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(lib.hs2_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
+        self._desc = desc
+        self._handle = handle
+
+    def release(self):
+        if self._handle is not None:
+            _cabi.lib().hs2_plan_destroy(self._handle)
+            self._handle = None
+        self._bufs = {}
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _buf(self, name, dtype=torch.float64, shape=None):
+        b = self._bufs.get(name)
+        shape = self.shape if shape is None else shape
+        if b is None or b.shape != torch.Size(shape):
+            b = torch.empty(shape, dtype=dtype, device=self._dev)
+            self._bufs[name] = b
+        return b
+
+    # ------------------------------------------------------------- sources
+    def _source(self, t, dt, volumetric_elements, volumetric):
+        """Evaluate the volumetric sources active at time ``t`` (reference
+        alternatingdirection_c_pyx.pyx:294-386).  Returns (Source struct or
+        None, keep-alive list)."""
+        from . import (IMPULSE_SOURCE, STEPPED_SOURCE, IMPULSE_POINT_SOURCE_JOULES,
+                       SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE, NO_SOURCE)
+        table = np.zeros(256)
+        dense = None
+        for idx, entry in enumerate(volumetric):
+            kind = entry[0]
+            if kind == NO_SOURCE:
+                continue
+            if kind == IMPULSE_SOURCE:
+                if t == entry[1]:
+                    table[idx] = entry[2] / dt
+            elif kind == STEPPED_SOURCE:
+                if t >= entry[1] and t <= entry[2]:
+                    table[idx] = entry[3]
+            elif kind == IMPULSE_POINT_SOURCE_JOULES:
+                if t == entry[1]:
+                    if np.ndim(self.volume_array) > 0:
+                        mask = _to_numpy(volumetric_elements) == idx
+                        dense = np.zeros(self.shape) if dense is None else dense
+                        dense[mask] = entry[2] / (np.asarray(self.volume_array)[mask] * dt)
+                    else:
+                        table[idx] = entry[2] / (self.volume_array * dt)
+            elif kind == SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE:
+                (_, impulse_time, decaydirec, offset, z_ndgrid, decay_dz, joulesperm2, characlength) = entry
+                if t == impulse_time:
+                    decaydirec = np.asarray(decaydirec, dtype=float)
+                    assert (decaydirec == np.array([1.0, 0.0, 0.0])).all() or (decaydirec == np.array([-1.0, 0.0, 0.0])).all()
+                    offset = float(offset)
+                    decay_dz = abs(float(decay_dz))
+                    joulesperm2 = float(joulesperm2)
+                    characlength = float(characlength)
+                    assert characlength > 0
+                    centre = np.asarray(z_ndgrid) * decaydirec[0] - offset
+                    left = centre - decay_dz / 2.0
+                    right = centre + decay_dz / 2.0
+                    use = (_to_numpy(volumetric_elements) == idx) & (right > 0.0)
+                    left = np.where(left < 0.0, 0.0, left)
+                    frac = -np.exp(-right[use] / characlength) + np.exp(-left[use] / characlength)
+                    dense = np.zeros(self.shape) if dense is None else dense
+                    dense[use] = frac * joulesperm2 / (decay_dz * dt)
+            else:
+                raise ValueError("unknown volumetric source type %r" % (kind,))
+        if not table.any() and dense is None:
+            return None, None
+        src = _cabi.Source()
+        keep = [table]
+        if table.any():
+            src.d_vol_elements = self._vol_elements_dev(volumetric_elements).data_ptr()
+            src.h_value = table.ctypes.data_as(_cabi.c_double_p)
+        if dense is not None:
+            d = torch.from_numpy(np.ascontiguousarray(dense)).to(self._dev)
+            keep.append(d)
+            src.d_dense = d.data_ptr()
+        return src, keep
+
+    def _vol_elements_dev(self, volumetric_elements):
+        if isinstance(volumetric_elements, torch.Tensor) and volumetric_elements.is_cuda:
+            if volumetric_elements.dtype != torch.uint8 or tuple(volumetric_elements.shape) != self.shape:
+                raise ValueError("volumetric_elements must be uint8 with the grid's shape")
+            return volumetric_elements.contiguous()
+        key = id(volumetric_elements)
+        if self._vol_dev is None or self._vol_key != key:
+            arr = _to_numpy(volumetric_elements)
+            if arr.dtype != np.uint8 or arr.shape != self.shape:
+                raise ValueError("volumetric_elements must be uint8 with the grid's shape")
+            self._vol_dev = torch.from_numpy(np.ascontiguousarray(arr)).to(self._dev)
+            self._vol_key = key
+            self._vol_ref = volumetric_elements       # pin the id
+        return self._vol_dev
+
+    # ------------------------------------------------------------- stepping
+    def step_device(self, T_in, T_out, t, dt, volumetric_elements, volumetric, halo_lo=None, halo_hi=None):
+        """One step on device tensors (float64, contiguous, plan's device).
+        ``T_out`` may be ``T_in``."""
+        self.ensure_device(T_in.device)
+        lib = _cabi.lib()
+        src, keep = (None, None)
+        if volumetric is not None and len(volumetric):
+            src, keep = self._source(t, dt, volumetric_elements, volumetric)
+        work = self._buf("work")
+        stream = torch.cuda.current_stream(self._dev).cuda_stream
+        rc = lib.hs2_step(self._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
+                          ctypes.byref(src) if src is not None else None,
+                          halo_lo.data_ptr() if halo_lo is not None else None,
+                          halo_hi.data_ptr() if halo_hi is not None else None,
+                          ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        if keep is not None and len(keep) > 1:
+            torch.cuda.current_stream(self._dev).synchronize()    # dense source buffer must outlive the launch
+        return T_out
+
+    def _check_field(self, T):
+        if tuple(T.shape) != self.shape:
+            raise ValueError("Tarray has shape %r, the plan was set up for %r" % (tuple(T.shape), self.shape))
+
+    def run_step(self, t, dt, Tarray, volumetric_elements, volumetric):
+        if isinstance(Tarray, torch.Tensor) and Tarray.is_cuda:
+            self._check_field(Tarray)
+            if Tarray.dtype != torch.float64:
+                raise ValueError("Tarray must be float64")
+            T_in = Tarray.contiguous()
+            with torch.cuda.device(T_in.device):
+                T_out = torch.empty_like(T_in)
+                return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
+        arr = np.ascontiguousarray(_to_numpy(Tarray), dtype=np.float64)
+        self._check_field(arr)
+        self.ensure_device()
+        with torch.cuda.device(self._dev):
+            stage_in = self._pinned("pin_in")
+            stage_in.copy_(torch.from_numpy(arr))
+            d_T = self._buf("T")
+            d_T.copy_(stage_in, non_blocking=True)
+            self.step_device(d_T, d_T, t, dt, volumetric_elements, volumetric)
+            stage_out = self._pinned("pin_out")
+            stage_out.copy_(d_T, non_blocking=True)
+            torch.cuda.current_stream(self._dev).synchronize()
+            return stage_out.numpy().copy()
+
+    def _pinned(self, name):
+        b = self._bufs.get(name)
+        if b is None:
+            b = torch.empty(self.shape, dtype=torch.float64).pin_memory()
+            self._bufs[name] = b
+        return b
+
+    # ------------------------------------------- host inspection (small grids)
+    def reference_matrices(self, stepnum):
+        """Materialise stage ``stepnum``'s A (n x 3), B, C (scipy CSR) and D in
+        the reference's permuted row order (alternatingdirection_c.c:114) from
+        the class tables - for inspection and tests on small grids."""
+        import scipy.sparse
+        from .alternatingdirection_c_pyx import _STAGES
+        if self.n > 4_000_000:
+            raise MemoryError("reference_matrices is meant for small grids")
+        perm = _STAGES[stepnum][1]
+        nz, ny, nx = self.shape
+        cid = self.class_id.cpu().numpy().astype(np.int64) & 0xFFFF
+        cc = self.class_coef[cid]                       # [nz,ny,nx,8]
+        M = cc[..., M_]
+        g = {2: (cc[..., GXM], cc[..., GXP]), 1: (cc[..., GYM], cc[..., GYP]), 0: (cc[..., GZM], cc[..., GZP])}
+        pshape = [self.shape[a] for a in perm]
+        idx = np.arange(self.n).reshape(pshape).transpose(np.argsort(perm))    # permuted flat index of cell (k,j,i)
+        sweep = perm[2]
+        # weight of each direction in B for this stage: 1 (not yet implicit) or 1/2
+        half = {2: 0.5, 1: 0.5 if stepnum >= 1 else 1.0, 0: 0.5 if stepnum >= 2 else 1.0}
+        A = np.zeros((self.n, 3))
+        A[idx.ravel(), 0] = (-0.5 * g[sweep][0]).ravel()
+        A[idx.ravel(), 2] = (-0.5 * g[sweep][1]).ravel()
+        A[idx.ravel(), 1] = (M + 0.5 * (g[sweep][0] + g[sweep][1])).ravel()
+        rows, cols, vals = [idx.ravel()], [idx.ravel()], [(M - sum(half[a] * (g[a][0] + g[a][1]) for a in range(3))).ravel()]
+        crow = {c: [[], [], []] for c in range(stepnum)}
+        axis_of_stage = {0: 2, 1: 1, 2: 0}
+        for c in range(stepnum):
+            a = axis_of_stage[c]
+            crow[c][0].append(idx.ravel()); crow[c][1].append(idx.ravel())
+            crow[c][2].append((-0.5 * (g[a][0] + g[a][1])).ravel())
+        for a in range(3):
+            for side, sgn in ((0, -1), (1, 1)):
+                gv = g[a][side]
+                sl_c = [slice(None)] * 3
+                sl_n = [slice(None)] * 3
+                sl_c[a] = slice(1, None) if sgn < 0 else slice(None, -1)
+                sl_n[a] = slice(None, -1) if sgn < 0 else slice(1, None)
+                r = idx[tuple(sl_c)].ravel()
+                cn = idx[tuple(sl_n)].ravel()
+                v = gv[tuple(sl_c)].ravel()
+                keep = v != 0.0
+                rows.append(r[keep]); cols.append(cn[keep]); vals.append(half[a] * v[keep])
+                for c in range(stepnum):
+                    if axis_of_stage[c] == a:
+                        crow[c][0].append(r[keep]); crow[c][1].append(cn[keep]); crow[c][2].append(0.5 * v[keep])
+        n = self.n
+        B = scipy.sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+        C = [scipy.sparse.coo_matrix((np.concatenate(crow[c][2]), (np.concatenate(crow[c][0]), np.concatenate(crow[c][1]))),
+                                     shape=(n, n)).tocsr() for c in range(stepnum)]
+        D = np.zeros(n)
+        D[idx.ravel()] = cc[..., D_].ravel()
+        return {"A": A, "B": B, "C": C, "D": D}
+
+
+def _to_numpy(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+def _unique_lines(cid, sub_lut, axis, n_sub):
+    """Group the lines of sweep ``axis`` by their sequence of row signatures.
+
+    cid: [nz,ny,nx] integer tensor of class ids; sub_lut: class -> row-signature
+    id.  Returns (line_id int32 [n_lines], reps int64 numpy [n_unique, L] of
+    signature ids).  Lines are hashed (64-bit polynomial) in z-chunks to bound
+    temporary memory, grouped by hash, and the grouping is then verified
+    exactly; a hash collision falls back to an exact row-wise unique."""
+    nz, ny, nx = cid.shape
+    dev = cid.device
+    L = (nx, ny, nz)[axis]
+    n_lines = cid.numel() // L
+    mult = 0x9E3779B97F4A7C15 - (1 << 64)          # odd 64-bit multiplier as int64
+    pw = torch.empty(L, dtype=torch.int64)
+    acc = 1
+    for r in range(L):
+        pw[r] = acc if acc < (1 << 63) else acc - (1 << 64)
+        acc = (acc * (mult & ((1 << 64) - 1)) + 0x632BE59BD9B4E019) & ((1 << 64) - 1)
+    pw = pw.to(dev)
+    chunk = max(1, int(32e6 // max(1, ny * nx)))
+    if axis == 2:
+        h = torch.zeros(ny * nx, dtype=torch.int64, device=dev)
+    else:
+        h = torch.empty(n_lines, dtype=torch.int64, device=dev)
+    for k0 in range(0, nz, chunk):
+        k1 = min(nz, k0 + chunk)
+        sub = sub_lut[cid[k0:k1].reshape(-1).long()].reshape(k1 - k0, ny, nx) + 1
+        if axis == 0:
+            h[k0 * ny:k1 * ny] = (sub * pw.view(1, 1, nx)).sum(dim=2).reshape(-1)
+        elif axis == 1:
+            h[k0 * nx:k1 * nx] = (sub * pw.view(1, ny, 1)).sum(dim=1).reshape(-1)
+        else:
+            h += (sub * pw[k0:k1].view(-1, 1, 1)).sum(dim=0).reshape(-1)
+    uh, inv = torch.unique(h, return_inverse=True)
+    nu = uh.numel()
+    # first line of every hash group
+    first = torch.full((nu,), n_lines, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inv, torch.arange(n_lines, device=dev), reduce="amin")
+    # order groups by first appearance so ids are deterministic
+    order = torch.argsort(first)
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(nu, device=dev)
+    line_id = rank[inv]
+    first = first[order]
+    sub_lines = _line_view(sub_lut[cid.reshape(-1).long()].reshape(nz, ny, nx).to(torch.int16 if n_sub < 32768 else torch.int32), axis)
+    reps = sub_lines[first]                                  # [nu, L]
+    # exact verification, chunked over lines
+    ok = True
+    step = max(1, int(64e6 // L))
+    for l0 in range(0, n_lines, step):
+        l1 = min(n_lines, l0 + step)
+        if not torch.equal(sub_lines[l0:l1], reps[line_id[l0:l1]]):
+            ok = False
+            break
+    if not ok:
+        reps, line_id = torch.unique(sub_lines, dim=0, return_inverse=True)
+    return line_id.to(torch.int32).contiguous(), reps.cpu().numpy().astype(np.int64)
+
+
+class CellwiseBuilder(object):
+    """Accumulates per-cell equations given one at a time through the
+    reference-style ``add_equation_to_adi_matrices`` and turns them into class
+    tables (small problems / custom assemblies)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        self.class_of_key = {}
+        self.coefs = []
+        self.class_id = np.full(self.shape, -1, dtype=np.int64)
+
+    def add(self, k, j, i, key, eqdicts):
+        from .alternatingdirection_c_pyx import class_coefficients
+        c = self.class_of_key.get(key)
+        if c is None:
+            M, g, D = class_coefficients(eqdicts)
+            c = self.class_of_key[key] = len(self.coefs)
+            self.coefs.append((M,) + tuple(g) + (D,))
+        self.class_id[k, j, i] = c
+
+    def finish(self, dt, volume_array):
+        if (self.class_id < 0).any():
+            raise ValueError("some cells have no equation")
+        return AdiPlan(self.shape, self.class_id, np.array(self.coefs), dt, volume_array)

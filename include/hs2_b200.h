@@ -1,0 +1,124 @@
+/* hs2_b200.h - C ABI of the B200-native ADI Crank-Nicolson time step.
+ *
+ * This is the drop-in boundary for heatsim2's hot path.  Every entry point
+ * names the reference interface it replaces (paths relative to the
+ * isuthermography/heatsim2 tree).  Plain pointers and sizes only; all device
+ * buffers are owned by the caller (the Python host layer hands in
+ * torch.Tensor.data_ptr() values), the plan owns nothing but a validated copy
+ * of its descriptor.  Kernels are launched on the CUDA stream passed in
+ * (a cudaStream_t cast to void*; NULL = legacy default stream) and never
+ * synchronise the device.
+ *
+ * Error convention: every function returns 0 on success or a negative
+ * HS2_E_* code; hs2_last_error() gives the message (thread-local).  Nothing
+ * calls abort()/exit() - the reference's assert/exit(1) paths
+ * (heatsim2/alternatingdirection_c.c:1-3,160-163) become error returns.
+ */
+#ifndef HS2_B200_H
+#define HS2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS2_ABI_VERSION 1
+
+#define HS2_OK 0
+#define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
+#define HS2_E_CUDA (-2)    /* a CUDA runtime call failed                      */
+#define HS2_E_NOMEM (-3)
+
+/* Per equation-class coefficient row (8 doubles), already divided by the
+ * capacity term M = rho*c/dt of the class (M = 1, g = 0, D = 0 for a
+ * TEMPERATURE_FIXED class):
+ *   [0] gx-/M  [1] gx+/M  [2] gy-/M  [3] gy+/M  [4] gz-/M  [5] gz+/M
+ *   [6] D/M    [7] M
+ * g are the face conductances (W/m^3/K) that heatsim2/crank_nicolson.pyx:
+ * 359-363 forms symbolically per cell; D is the volumetric-source weight
+ * (heatsim2/alternatingdirection_c.c:119-121).                              */
+#define HS2_COEF_STRIDE 8
+
+/* Per unique tridiagonal line, per row: {1/pivot, lower/pivot, upper/pivot, 0}
+ * of the Thomas factorisation of (I - 1/2 M^-1 L_axis) - the information
+ * heatsim2/tridiag.pyx:9-43 (tridiaglu) stores as Lmat/Umat, 72 B per row
+ * there, 32 B per row of a *unique* line here.                              */
+#define HS2_LU_STRIDE 4
+
+/* Axis numbering used by every per-axis array: 0 = x (contiguous), 1 = y,
+ * 2 = z (slowest).  Line numbering: x-lines k*ny+j, y-lines k*nx+i,
+ * z-lines j*nx+i.                                                            */
+typedef struct hs2_plan_desc {
+  int64_t nz, ny, nx;          /* local grid (a z-slab in multi-GPU runs)     */
+  int32_t n_classes;
+  int32_t class_id_bytes;      /* 1 (u8) or 2 (u16)                           */
+  const void *d_class_id;      /* device, [nz][ny][nx]                        */
+  const double *d_class_coef;  /* device, [n_classes][HS2_COEF_STRIDE]        */
+  const uint32_t *d_line_id[3];/* device, unique-line id of every line        */
+  const double *d_line_lu[3];  /* device, [n_unique][L_axis][HS2_LU_STRIDE]   */
+  int32_t n_unique[3];
+  int32_t device;              /* CUDA device ordinal the buffers live on     */
+} hs2_plan_desc;
+
+typedef struct hs2_plan hs2_plan;
+
+/* Volumetric source of one step (replaces the per-call volumetric_array of
+ * heatsim2/alternatingdirection_c_pyx.pyx:294-386).  Either field may be
+ * NULL.  Table form: src(cell) = value[vol_elements(cell)] with a 256-entry
+ * host table (IMPULSE / STEPPED / POINT_JOULES with scalar volume); dense
+ * form: a full [nz][ny][nx] device array in W/m^3 (z-decaying impulse,
+ * per-cell volumes).                                                          */
+typedef struct hs2_source {
+  const uint8_t *d_vol_elements; /* device [nz][ny][nx] or NULL               */
+  const double *h_value;         /* host [256] or NULL                        */
+  const double *d_dense;         /* device [nz][ny][nx] or NULL               */
+} hs2_source;
+
+int hs2_abi_version(void);
+const char *hs2_last_error(void);
+
+/* replaces create_adi_step x3 + finalize (alternatingdirection_c.h:52,
+ * alternatingdirection_c_pyx.pyx:212-282)                                     */
+int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out);
+/* replaces delete_adi_step (alternatingdirection_c.h:50)                      */
+int hs2_plan_destroy(hs2_plan *plan);
+
+/* One ADI time step = run_adi_steps (alternatingdirection_c_pyx.pyx:287-416).
+ *   d_T_in   [nz][ny][nx]  field at t - dt/2
+ *   d_T_out  [nz][ny][nx]  field at t + dt/2 (may alias d_T_in)
+ *   d_work   [nz][ny][nx]  scratch (stage increments)
+ *   src      source of this step or NULL
+ *   d_halo_lo / d_halo_hi: [ny][nx] planes of T_in just below k=0 / above
+ *            k=nz-1 owned by the neighbouring slab, or NULL at a domain face. */
+int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out,
+             double *d_work, const hs2_source *src, const double *d_halo_lo,
+             const double *d_halo_hi, void *stream);
+
+/* The three stages separately (multi-GPU drivers interleave communication).
+ * hs2_sweep_x: d_work = (M - Lx/2)^-1 [(Lx+Ly+Lz) T_in + D src]
+ * hs2_sweep_y: d_work = (M - Ly/2)^-1 M d_work
+ * hs2_sweep_z: d_T_out = d_T_in + (M - Lz/2)^-1 M d_work   (local z lines)   */
+int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work,
+                const hs2_source *src, const double *d_halo_lo,
+                const double *d_halo_hi, void *stream);
+int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream);
+int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out,
+                double *d_work, void *stream);
+
+/* Drop-ins for heatsim2/tridiag.pyx on device arrays.
+ * hs2_tridiag_lu    = tridiaglu   (:9-43):  A[n][3] -> L[n][3], U[n][3]
+ * hs2_tridiag_solve = tridiagsolve(:46-69): x = U^-1 L^-1 b, one chain of n
+ * rows, evaluated as a parallel scan of the two first-order recurrences.
+ * d_scratch: at least hs2_tridiag_scratch_bytes(n) bytes.                    */
+int64_t hs2_tridiag_scratch_bytes(int64_t n);
+int hs2_tridiag_lu(int64_t n, const double *d_A, double *d_L, double *d_U,
+                   void *d_scratch, void *stream);
+int hs2_tridiag_solve(int64_t n, const double *d_L, const double *d_U,
+                      const double *d_b, double *d_x, void *d_scratch,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS2_B200_H */
