@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/*.npz from the UNMODIFIED
+reference (built into oracle/_ref by oracle/build_ref.py from /root/reference).
+
+Run in the build container (the GPU box has no /root/reference; it only reads
+the committed .npz files):
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+Each file holds, for one tests/problems.py configuration, the field after the
+listed step counts (``T_<n>``), the whole-run history at the probe cells
+(``probe_hist``, when the problem names probes) and ``sum_<n>``; inputs are NOT
+stored - they are rebuilt from tests/problems.py with the recorded kwargs.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import problems      # noqa: E402
+import ref_loader    # noqa: E402
+
+# name -> (problem, kwargs, steps whose full field is stored)
+CASES = {
+    "c1_steelonfoam": ("steelonfoam", dict(nsteps=999), (1, 10, 100, 999)),
+    "c2_uniform_32": ("uniform_slab", dict(n=32, nsteps=200), (1, 10, 200)),
+    "c2_uniform_ragged": ("uniform_slab", dict(shape=(19, 33, 45), nsteps=20), (1, 20)),
+    "c3_steelonwater": ("steelonwater", dict(nz=80, ny=20, nx=24, nsteps=100), (1, 10, 100)),
+    "c4_composite": ("composite", dict(nz=32, ny=32, nx=48, ply=8, nsteps=100), (1, 10, 100)),
+    "sources_demo": ("sources_demo", dict(), (1, 2, 3, 4, 5, 6)),
+    "line_1d": ("uniform_slab", dict(shape=(1, 1, 40), nsteps=5), (1, 5)),
+    "plane_2d": ("uniform_slab", dict(shape=(1, 24, 20), nsteps=5), (1, 5)),
+}
+
+
+def main():
+    ref = ref_loader.load()
+    if ref is None:
+        raise SystemExit("reference not built: run python oracle/build_ref.py first")
+    for case, (pname, kwargs, steps) in CASES.items():
+        prob = problems.ALL[pname](ref, **kwargs)
+        P, S = ref_loader.quiet_setup(ref, *prob["setup_args"])
+        T = np.array(prob["T0"], dtype=np.float64)
+        out = {"meta": json.dumps({"problem": pname, "kwargs": kwargs, "steps": list(steps)})}
+        probes = prob.get("probes")
+        hist = []
+        for it in range(prob["nsteps"]):
+            T = ref.run_adi_steps(P, S, prob["t0"] + prob["dt"] * it, prob["dt"], T,
+                                  prob["volumetric_elements"], prob["volumetric"])
+            if probes:
+                hist.append([T[p] for p in probes])
+            if (it + 1) in steps:
+                # the big C1 fields are stored for two steps only
+                if case != "c1_steelonfoam" or (it + 1) in (10, 100):
+                    out["T_%d" % (it + 1)] = T.copy()
+                out["sum_%d" % (it + 1)] = T.sum()
+                if probes:
+                    out["probe_%d" % (it + 1)] = np.array([T[p] for p in probes])
+        if probes:
+            out["probe_hist"] = np.array(hist)
+        np.savez_compressed(os.path.join(HERE, case + ".npz"), **out)
+        print(case, prob["shape"], prob["nsteps"], "steps")
+
+
+if __name__ == "__main__":
+    main()
