@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py - ADI cell-updates/s (float64) of the B200 path, with roofline,
+end-to-end and CPU-baseline figures, as ONE JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1] recipe at north_star's target size):
+uniform isotropic steel slab, insulating outer faces, conducting interior,
+dz=dy=dx=1e-4, dt=0.01, T0 = default_rng(1234).random(shape), flash on layer
+0 at t=0 (outside the timed region: the timed steps are source-free steps, as
+999 of the 1000 steps of the config are).  N=1: 512^3.  N>1 (weak scaling,
+134 M cells per GPU, z-slab decomposition): 2 -> 1024x512x512,
+4 -> 1024x1024x512, 8 -> 1024^3 (north_star's multi-GPU grid).
+
+A "step" is one full ADI time step (x-, y-, z-sweep).  All three field arrays
+are 1.07 GB each, far larger than the 126 MB L2, so no explicit flush is needed
+between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "ADI cell-updates/s (float64)"
+UNIT = "cell-updates/s"
+BYTES_PER_CELL = {"x": 16, "y": 16, "z": 24}        # 56 B per cell-update
+
+
+def grid_for(n_gpus, g):
+    if n_gpus == 1:
+        return (g, g, g)
+    # weak scaling: g^3 cells per GPU
+    return {2: (2 * g, g, g), 4: (2 * g, 2 * g, g), 8: (2 * g, 2 * g, 2 * g)}[n_gpus]
+
+
+# ----------------------------------------------------------------- clock log
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1])
+                smax = float(f[2])
+            except ValueError:
+                continue
+            if t_begin - 0.05 <= ts <= t_end + 0.05:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------- CPU baselines
+def _ref_replica(grid, steps, warmup, conn):
+    """one process: the unmodified reference on a grid^3 sample of the workload"""
+    import numpy as np
+    import problems
+    import ref_loader
+    ref = ref_loader.load()
+    prob = problems.uniform_slab(ref, n=grid)
+    t0 = time.perf_counter()
+    P, S = ref_loader.quiet_setup(ref, *prob["setup_args"])
+    t_setup = time.perf_counter() - t0
+    T = np.array(prob["T0"])
+    it = 0
+    for _ in range(warmup):
+        T = ref.run_adi_steps(P, S, prob["dt"] * it, prob["dt"], T, prob["volumetric_elements"], prob["volumetric"])
+        it += 1
+    conn.send(("ready", t_setup))
+    conn.recv()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T = ref.run_adi_steps(P, S, prob["dt"] * it, prob["dt"], T, prob["volumetric_elements"], prob["volumetric"])
+        it += 1
+    conn.send(("done", time.perf_counter() - t0))
+
+
+def time_reference(grid, steps, warmup, replicas):
+    """Reference Cython/C path (oracle/_ref) on `replicas` host processes, each
+    stepping its own grid^3 uniform slab.  Returns cells/s (aggregate), secs."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    procs = []
+    for _ in range(replicas):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_ref_replica, args=(grid, steps, warmup, b))
+        pr.start()
+        procs.append((pr, a))
+    setups = [a.recv()[1] for _, a in procs]
+    for _, a in procs:
+        a.send("go")
+    times = [a.recv()[1] for _, a in procs]
+    for pr, _ in procs:
+        pr.join()
+    cells = replicas * steps * grid ** 3
+    return cells / max(times), max(times), max(setups)
+
+
+def time_oracle_port(grid, steps, warmup):
+    import numpy as np
+    import adi_oracle
+    import problems
+    import heatsim2_b200 as hs
+    prob = problems.uniform_slab(hs, n=grid)
+    O = adi_oracle.setup(*prob["setup_args"])
+    T = np.array(prob["T0"])
+    for it in range(warmup):
+        T = O.step(prob["dt"] * it, prob["dt"], T)
+    t0 = time.perf_counter()
+    for it in range(steps):
+        T = O.step(prob["dt"] * (warmup + it), prob["dt"], T)
+    el = time.perf_counter() - t0
+    return steps * grid ** 3 / el, el
+
+
+def cpu_baseline(sample_grid=64, steps=20, warmup=2):
+    import ref_loader
+    if ref_loader.available():
+        v, el, su = time_reference(sample_grid, steps, warmup, 1)
+        return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": "unmodified reference (oracle/_ref) run_adi_steps, %d steps of the same recipe at %d^3 "
+                          "(larger grids need 1.5 kB/cell of host RAM); setup %.1f s not timed" % (steps, sample_grid, su),
+                "host_cpus": os.cpu_count()}
+    v, el = time_oracle_port(sample_grid, steps, warmup)
+    return {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "numpy oracle, %d steps at %d^3" % (steps, sample_grid), "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ref_loader
+    grid = 64
+    if ref_loader.available():
+        replicas = max(1, min(os.cpu_count() or 1, 32))
+        v, el, su = time_reference(grid, args.steps, args.warmup, replicas)
+        kind, cores = "reference", replicas
+        sample = ("unmodified reference (oracle/_ref), %d independent single-threaded replicas (the reference has no "
+                  "threading), each %d steps of the workload recipe at %d^3" % (replicas, args.steps, grid))
+    else:
+        v, el = time_oracle_port(grid, args.steps, args.warmup)
+        kind, cores = "port", 1
+        sample = "numpy oracle port, %d steps at %d^3" % (args.steps, grid)
+    shape = grid_for(args.gpus, args.grid)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(shape), "grid": list(shape), "sample_grid": [grid] * 3},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(shape):
+    return ("uniform isotropic steel slab %dx%dx%d (z,y,x), insulating faces, dt=0.01, random T0 seed 1234 "
+            "(BASELINE configs[1] recipe at the north_star target size)" % shape)
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200_single(args):
+    import numpy as np
+    import torch
+    import heatsim2_b200 as hs
+    from heatsim2_b200 import _cabi
+    import problems
+    _cabi.lib()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    shape = grid_for(1, args.grid)
+    t0 = time.perf_counter()
+    prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
+    P, S = hs.setup(*prob["setup_args"])
+    plan = P.plan
+    plan.ensure_device(dev)
+    setup_s = time.perf_counter() - t0
+    n = plan.n
+    rng = np.random.default_rng(1234)
+    T_host = torch.empty(shape, dtype=torch.float64).pin_memory()
+    T_host.numpy()[...] = rng.random(shape)
+    Ta = T_host.to(dev)
+    Tb = torch.empty_like(Ta)
+    dt = prob["dt"]
+    ve, vol = prob["volumetric_elements"], prob["volumetric"]
+    # step 0 carries the flash (source path), outside the timed region
+    hs.run_adi_steps(P, S, 0.0, dt, Ta, ve, vol, out=Tb)
+    Ta, Tb = Tb, Ta
+    it = 1
+    for _ in range(max(args.warmup, 3)):
+        hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+        Ta, Tb = Tb, Ta
+        it += 1
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- value: K device-resident steps through the public API
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    tb = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+        Ta, Tb = Tb, Ta
+        it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    # ---- per-kernel: same steps as three C-ABI calls with events between them
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        plan.timed_sweeps(Ta, Tb, evs[k])
+        Ta, Tb = Tb, Ta
+    torch.cuda.synchronize()
+    te = time.time()
+    clocks = sampler.stop(tb, te)
+    sweep_ms = {}
+    for si, name in enumerate("xyz"):
+        sweep_ms[name] = sum(e[si].elapsed_time(e[si + 1]) for e in evs) / args.steps
+    ms_step = ms_total / args.steps
+    value = n / (ms_step * 1e-3)
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peak, peak_src = json.load(open(pk_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(sweep_ms, key=lambda k: sweep_ms[k])
+    ach = BYTES_PER_CELL[dom] * n / (sweep_ms[dom] * 1e-3) / 1e9
+    kernels = {k: {"ms": sweep_ms[k], "algorithmic_bytes": BYTES_PER_CELL[k] * n,
+                   "GBps": BYTES_PER_CELL[k] * n / (sweep_ms[k] * 1e-3) / 1e9,
+                   "frac": BYTES_PER_CELL[k] * n / (sweep_ms[k] * 1e-3) / 1e9 / peak} for k in sweep_ms}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "hbm", "kernel": "sweep_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "step": {"algorithmic_bytes": 56 * n, "GBps": 56 * n / (ms_step * 1e-3) / 1e9,
+                         "frac": 56 * n / (ms_step * 1e-3) / 1e9 / peak, "frac_of_8TBps_nominal": 56 * n / (ms_step * 1e-3) / 8e12},
+                "kernels": kernels}
+    # ---- e2e: host buffers in and out of run_adi_steps every step (pinned)
+    H_in = T_host
+    H_out = torch.empty(shape, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        hs.run_adi_steps(P, S, it * dt, dt, H_in, ve, vol, out=H_out)
+        H_in, H_out = H_out, H_in
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(e2e_steps):
+        hs.run_adi_steps(P, S, it * dt, dt, H_in, ve, vol, out=H_out)
+        H_in, H_out = H_out, H_in
+        it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+           "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "heatsim2_b200.run_adi_steps(host float64 tensor [pinned] -> host tensor)"}
+    assert bool(torch.isfinite(Ta).all())
+    base = cpu_baseline() if not args.no_cpu_baseline else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(shape), "grid": list(shape), "cells": n,
+                       "l2": "inputs larger than L2 (3 arrays of %.2f GB vs 126 MB)" % (n * 8 / 1e9),
+                       "classes": plan.n_classes, "unique_lines": list(plan.n_unique), "setup_s": setup_s},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+            "gpu_launches": args.steps * plan.launches_per_step, "clocks": clocks}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.gpus == 1:
+        return run_b200_single(args)
+    from heatsim2_b200 import dist_bench
+    return dist_bench.run(args, grid_for(args.gpus, args.grid), workload_name)
+
+
+if __name__ == "__main__":
+    main()

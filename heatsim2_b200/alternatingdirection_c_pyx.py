@@ -241,14 +241,17 @@ def add_equation_to_adi_matrices(ADI_params, ADI_steps, k, j, i, key_params, aet
     builder.add(k, j, i, key_params, eqdicts)
 
 
-def run_adi_steps(ADI_params, ADI_steps, t, dt, Tarray, volumetric_elements, volumetric):
+def run_adi_steps(ADI_params, ADI_steps, t, dt, Tarray, volumetric_elements, volumetric, out=None):
     """Advance ``Tarray`` (indexed [z,y,x], float64) by one ADI time step.
 
     Same call as the reference (:287-416).  ``Tarray`` may be a numpy array -
     it is copied to the device, stepped, and a new numpy array is returned,
     like the reference - or a CUDA ``torch.Tensor``, in which case the result
-    is a new CUDA tensor and nothing crosses PCIe."""
+    is a new CUDA tensor and nothing crosses PCIe.  A host ``torch.Tensor``
+    (pinned for full PCIe speed) is copied in and a host tensor comes back.
+    ``out`` (extension) receives the result instead of a fresh allocation; for
+    device tensors it may be ``Tarray`` itself."""
     plan = ADI_params.plan
     if plan is None:
         raise RuntimeError("ADI_params carries no plan; it must come from heatsim2_b200.setup()")
-    return plan.run_step(t, dt, Tarray, volumetric_elements, volumetric)
+    return plan.run_step(t, dt, Tarray, volumetric_elements, volumetric, out=out)

@@ -275,7 +275,13 @@ def setup(z0, y0, x0,
             row = expression_cache[value_key] = (M,) + tuple(g) + (D,)
         coefs[c] = row
 
+    # distinct keys can yield the same equation (e.g. a different neighbour
+    # behind an insulating face): merge them so the tables stay minimal
+    ucoefs, merged = np.unique(coefs, axis=0, return_inverse=True)
+    if len(ucoefs) < len(coefs):
+        lut = torch.from_numpy(merged.reshape(-1).astype(np.int32)).to(class_id.device)
+        class_id = lut[class_id.long()]
+        coefs = ucoefs
     ADI_params.plan = AdiPlan((nz, ny, nx), class_id, coefs, dt, volume_array, volumetric_elements=vol,
                               materials=materials)
-    ADI_params.class_keys = keys
     return (ADI_params, ADI_steps)

@@ -119,6 +119,11 @@ class AdiPlan(object):
             self.line_lu.append(thomas_factors(lo, dg, hi))
 
     @property
+    def launches_per_step(self):
+        """kernels launched by one hs2_step (x: rhs + solve, y, z)"""
+        return 4
+
+    @property
     def n_unique(self):
         return tuple(int(t.shape[0]) for t in self.line_lu)
 
@@ -276,14 +281,46 @@ class AdiPlan(object):
         if tuple(T.shape) != self.shape:
             raise ValueError("Tarray has shape %r, the plan was set up for %r" % (tuple(T.shape), self.shape))
 
-    def run_step(self, t, dt, Tarray, volumetric_elements, volumetric):
+    def timed_sweeps(self, T_in, T_out, events):
+        """One source-free step as three separate C-ABI calls with CUDA events
+        recorded on the launching stream between them (bench.py's per-kernel
+        roofline).  ``events`` = 4 torch.cuda.Event(enable_timing=True)."""
+        self.ensure_device(T_in.device)
+        lib = _cabi.lib()
+        work = self._buf("work")
+        ts = torch.cuda.current_stream(self._dev)
+        stream = ctypes.c_void_p(ts.cuda_stream)
+        events[0].record(ts)
+        _cabi.check(lib.hs2_sweep_x(self._handle, T_in.data_ptr(), work.data_ptr(), None, None, None, stream))
+        events[1].record(ts)
+        _cabi.check(lib.hs2_sweep_y(self._handle, work.data_ptr(), stream))
+        events[2].record(ts)
+        _cabi.check(lib.hs2_sweep_z(self._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(), stream))
+        events[3].record(ts)
+
+    def run_step(self, t, dt, Tarray, volumetric_elements, volumetric, out=None):
+        if isinstance(Tarray, torch.Tensor) and not Tarray.is_cuda:
+            # host tensor (ideally pinned) in -> host tensor out, no staging copies
+            self._check_field(Tarray)
+            if Tarray.dtype != torch.float64 or not Tarray.is_contiguous():
+                raise ValueError("Tarray must be a contiguous float64 tensor")
+            self.ensure_device()
+            with torch.cuda.device(self._dev):
+                d_T = self._buf("T")
+                d_T.copy_(Tarray, non_blocking=True)
+                self.step_device(d_T, d_T, t, dt, volumetric_elements, volumetric)
+                if out is None:
+                    out = torch.empty(self.shape, dtype=torch.float64).pin_memory()
+                out.copy_(d_T, non_blocking=True)
+                torch.cuda.current_stream(self._dev).synchronize()
+            return out
         if isinstance(Tarray, torch.Tensor) and Tarray.is_cuda:
             self._check_field(Tarray)
             if Tarray.dtype != torch.float64:
                 raise ValueError("Tarray must be float64")
             T_in = Tarray.contiguous()
             with torch.cuda.device(T_in.device):
-                T_out = torch.empty_like(T_in)
+                T_out = torch.empty_like(T_in) if out is None else out
                 return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
         arr = np.ascontiguousarray(_to_numpy(Tarray), dtype=np.float64)
         self._check_field(arr)
