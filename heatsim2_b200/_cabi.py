@@ -17,13 +17,22 @@ c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
+class AxisTables(ctypes.Structure):
+    _fields_ = [
+        ("d_line_id", c_void_p), ("d_lu", c_void_p),
+        ("d_tab", c_void_p), ("d_GE", c_void_p),
+        ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
+        ("pitch", ctypes.c_int32),
+    ]
+
+
 class PlanDesc(ctypes.Structure):
     _fields_ = [
         ("nz", ctypes.c_int64), ("ny", ctypes.c_int64), ("nx", ctypes.c_int64),
         ("n_classes", ctypes.c_int32), ("class_id_bytes", ctypes.c_int32),
         ("d_class_id", c_void_p), ("d_class_coef", c_void_p),
-        ("d_line_id", c_void_p * 3), ("d_line_lu", c_void_p * 3),
-        ("n_unique", ctypes.c_int32 * 3), ("device", ctypes.c_int32),
+        ("axis", AxisTables * 3),
+        ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
 
 
@@ -43,6 +52,7 @@ PROTOTYPES = {
     "hs2_last_error": (ctypes.c_char_p, []),
     "hs2_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.POINTER(c_void_p)]),
     "hs2_plan_destroy": (ctypes.c_int, [c_void_p]),
+    "hs2_plan_launches_per_step": (ctypes.c_int, [c_void_p]),
     "hs2_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_y": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),

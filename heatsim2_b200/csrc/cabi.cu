@@ -29,7 +29,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
               "hs2_plan_create: n_classes %d out of range for %d-byte ids", desc->n_classes, desc->class_id_bytes);
   HS2_REQUIRE(desc->d_class_id && desc->d_class_coef, "hs2_plan_create: NULL class tables");
   for (int a = 0; a < 3; ++a)
-    HS2_REQUIRE(desc->d_line_id[a] && desc->d_line_lu[a] && desc->n_unique[a] > 0,
+    HS2_REQUIRE(desc->axis[a].d_line_id && desc->axis[a].d_lu && desc->axis[a].n_unique > 0,
                 "hs2_plan_create: missing line table for axis %d", a);
   int ndev = 0;
   HS2_CUDA_CHECK(cudaGetDeviceCount(&ndev));
@@ -57,6 +57,11 @@ int hs2_plan_destroy(hs2_plan *plan) {
   return HS2_OK;
 }
 
+int hs2_plan_launches_per_step(const hs2_plan *plan) {
+  if (!plan) return 0;
+  return (hs2_tile_supported(plan, 0) ? 1 : 2) + 2;
+}
+
 int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src, const double *d_halo_lo,
                 const double *d_halo_hi, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
@@ -66,11 +71,13 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
 
 int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream) {
   HS2_REQUIRE(plan && d_work, "hs2_sweep_y: NULL argument");
+  if (hs2_tile_supported(plan, 1)) return hs2_tile_sweep_y(plan, d_work, (cudaStream_t)stream);
   return hs2_v1_sweep_y(plan, d_work, (cudaStream_t)stream);
 }
 
 int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_T_out && d_work, "hs2_sweep_z: NULL argument");
+  if (hs2_tile_supported(plan, 2)) return hs2_tile_sweep_z(plan, d_T_in, d_T_out, d_work, (cudaStream_t)stream);
   return hs2_v1_sweep_z(plan, d_T_in, d_T_out, d_work, (cudaStream_t)stream);
 }
 

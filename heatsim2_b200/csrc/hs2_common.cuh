@@ -39,3 +39,8 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
                    const double *halo_lo, const double *halo_hi, cudaStream_t st);
 int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
+
+// kernels_strided.cu / kernels_x.cu - register/shared-memory tile kernels
+bool hs2_tile_supported(const hs2_plan *p, int axis);
+int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
+int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);

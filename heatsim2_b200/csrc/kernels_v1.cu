@@ -125,7 +125,7 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
                                                      dense, halo_lo, halo_hi, d.nz, d.ny, d.nx);
   HS2_CUDA_CHECK(cudaGetLastError());
   const int64_t n_lines = d.nz * d.ny;
-  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, nullptr, nullptr, d.d_line_id[0], d.d_line_lu[0],
+  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, nullptr, nullptr, d.axis[0].d_line_id, d.axis[0].d_lu,
                                                                    n_lines, d.nx, 1, 1, d.nx);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
@@ -134,7 +134,7 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
 int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st) {
   const hs2_plan_desc &d = p->d;
   const int64_t n_lines = d.nz * d.nx;
-  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, nullptr, nullptr, d.d_line_id[1], d.d_line_lu[1],
+  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, nullptr, nullptr, d.axis[1].d_line_id, d.axis[1].d_lu,
                                                                    n_lines, d.ny, d.nx, d.nx, d.ny * d.nx);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
@@ -143,7 +143,7 @@ int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st) {
 int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st) {
   const hs2_plan_desc &d = p->d;
   const int64_t n_lines = d.ny * d.nx;
-  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, T, Tout, d.d_line_id[2], d.d_line_lu[2], n_lines,
+  thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, T, Tout, d.axis[2].d_line_id, d.axis[2].d_lu, n_lines,
                                                                    d.nz, d.ny * d.nx, n_lines, 0);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;

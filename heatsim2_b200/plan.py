@@ -13,6 +13,7 @@ torch tensors are used as device buffers only; every kernel launch goes through
 the C ABI (``_cabi``).  Nothing here computes a time step on the CPU.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -53,6 +54,91 @@ def thomas_factors(lo, dg, hi):
     return out
 
 
+def choose_chunk(L):
+    """Rows per chunk M and chunk count P for a line of length L.  The kernels
+    hold M doubles per thread in registers and run P*W threads per tile
+    (W = 16 or 8 adjacent lines): M=8 with up to 16 chunks, M=16 with up to 32,
+    M=32 with up to 32.  The smallest valid M is taken, except that lines
+    longer than 256 rows use HS2_CHUNK (default 16) when it is valid.
+    (0, 0): too long for the register-tile kernels (whole-line fallback)."""
+    valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
+    if not valid:
+        return 0, 0
+    if L > 256:
+        pref = int(os.environ.get("HS2_CHUNK", "16"))
+        for M, P in valid:
+            if M == pref:
+                return M, P
+    return valid[0]
+
+
+T_INV, T_F, T_C, T_S, T_CP, T_PLANES = 0, 1, 2, 3, 4, 5
+
+
+def chunk_factors(lo, dg, hi, M):
+    """Tables of the partitioned (SPIKE-type) tridiagonal solve for a batch of
+    unique lines [n_unique, L] cut into chunks of M rows.
+
+    Per chunk, with the coupling to the neighbouring chunks moved to the right
+    hand side (alpha = x just before the chunk, beta = x just after it):
+      forward   u_k = d_k*inv_k - f_k*u_{k-1}            (u_{-1} = 0)
+      first row y_f = sum_k c_k u_k ,  last row y_l = u_last
+      backward  x_k = (u_k - alpha*s_k) - cp_k*x_{k+1}   (x_last = E known)
+    tab[nu, 5, pitch]: planes inv, f, c, s, cp (pitch = L rounded up to 4).
+    The first/last values (F_p, E_p) of all chunks of a line solve a 2P x 2P
+    system whose matrix depends on the line only; GE[nu, P, 2P] holds, for
+    every chunk, the row of its inverse that gives E_p from the interleaved
+    right hand side (y_f0, y_l0, y_f1, y_l1, ...).  alpha_p = E_{p-1}."""
+    nu, L = dg.shape
+    P = -(-L // M)
+    pitch = -(-L // 4) * 4
+    tab = np.zeros((nu, T_PLANES, pitch))
+    tab[:, T_INV, :] = 1.0
+    v0 = np.zeros((nu, P))
+    cm = np.zeros((nu, P))
+    sl = np.zeros((nu, P))
+    cpl = np.zeros((nu, P))
+    for p in range(P):
+        r0, r1 = p * M, min(L, (p + 1) * M)
+        cp_prev = np.zeros(nu)
+        s_prev = np.zeros(nu)
+        c_cur = np.ones(nu)
+        acc = np.zeros(nu)
+        for r in range(r0, r1):
+            piv = dg[:, r] - (lo[:, r] * cp_prev if r > r0 else 0.0)
+            inv = 1.0 / piv
+            f = lo[:, r] * inv
+            cp = hi[:, r] * inv
+            s = f if r == r0 else -f * s_prev
+            tab[:, T_INV, r] = inv
+            tab[:, T_F, r] = f if r > r0 else 0.0    # the kernel's recurrence restarts at a chunk start
+            tab[:, T_C, r] = c_cur
+            tab[:, T_S, r] = s
+            tab[:, T_CP, r] = cp
+            acc += c_cur * s
+            c_cur = -cp * c_cur
+            cp_prev, s_prev = cp, s
+        v0[:, p], cm[:, p], sl[:, p], cpl[:, p] = acc, c_cur, s_prev, cp_prev
+    # reduced system, unknown order [F_0..F_{P-1}, E_0..E_{P-1}]:
+    #   F_p + v0_p E_{p-1} - cm_p F_{p+1} = yf_p ;  E_p + sl_p E_{p-1} + cpl_p F_{p+1} = yl_p
+    R = np.zeros((nu, 2 * P, 2 * P))
+    idx = np.arange(P)
+    R[:, idx, idx] = 1.0
+    R[:, P + idx, P + idx] = 1.0
+    for p in range(P):
+        if p > 0:
+            R[:, p, P + p - 1] = v0[:, p]
+            R[:, P + p, P + p - 1] = sl[:, p]
+        if p < P - 1:
+            R[:, p, p + 1] = -cm[:, p]
+            R[:, P + p, p + 1] = cpl[:, p]
+    Rinv = np.linalg.inv(R)
+    GE = np.zeros((nu, P, 2 * P))
+    GE[:, :, 0::2] = Rinv[:, P:, :P]
+    GE[:, :, 1::2] = Rinv[:, P:, P:]
+    return tab, GE
+
+
 class AdiPlan(object):
     def __init__(self, shape, class_id, class_coef, dt, volume_array, volumetric_elements=None,
                  materials=None):
@@ -76,6 +162,8 @@ class AdiPlan(object):
         self._build_lines()
         self._dev = None
         self._handle = None
+        # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
+        self.flags = 1 if os.environ.get("HS2_FORCE_FALLBACK", "0") == "1" else 0
         self._bufs = {}
         self._vol_dev = None
         self._vol_key = None
@@ -106,6 +194,7 @@ class AdiPlan(object):
         cid = self.class_id
         cid_i = (cid.to(torch.int32) & 0xFFFF) if cid.dtype == torch.int16 else cid
         self.line_id, self.line_lu, self.line_rows = [], [], []
+        self.chunk, self.chunk_tabs = [], []
         for axis in range(3):
             gm, gp = _AXIS_G[axis]
             rows = np.stack([-0.5 * cc[:, gm] / M, 1.0 + 0.5 * (cc[:, gm] + cc[:, gp]) / M, -0.5 * cc[:, gp] / M], axis=1)
@@ -117,11 +206,15 @@ class AdiPlan(object):
             self.line_id.append(lid)                       # int32 tensor [n_lines]
             self.line_rows.append((lo, dg, hi))            # numpy [n_unique, L] each
             self.line_lu.append(thomas_factors(lo, dg, hi))
+            rows_per_chunk, n_chunks = choose_chunk(dg.shape[1])
+            self.chunk.append((rows_per_chunk, n_chunks))
+            self.chunk_tabs.append(chunk_factors(lo, dg, hi, rows_per_chunk) if rows_per_chunk else None)
 
     @property
     def launches_per_step(self):
-        """kernels launched by one hs2_step (x: rhs + solve, y, z)"""
-        return 4
+        """kernels launched by one hs2_step"""
+        self.ensure_device()
+        return int(_cabi.lib().hs2_plan_launches_per_step(self._handle))
 
     @property
     def n_unique(self):
@@ -144,6 +237,8 @@ class AdiPlan(object):
         self.d_coef = torch.from_numpy(self.scaled_coef).to(dev)
         self.d_line_id = [t.to(dev).contiguous() for t in self.line_id]
         self.d_line_lu = [torch.from_numpy(t).to(dev).contiguous() for t in self.line_lu]
+        self.d_chunk = [None if t is None else [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in t]
+                        for t in self.chunk_tabs]
         desc = _cabi.PlanDesc()
         desc.nz, desc.ny, desc.nx = self.shape
         desc.n_classes = self.n_classes
@@ -151,10 +246,16 @@ class AdiPlan(object):
         desc.d_class_id = self.d_class_id.data_ptr()
         desc.d_class_coef = self.d_coef.data_ptr()
         for a in range(3):
-            desc.d_line_id[a] = self.d_line_id[a].data_ptr()
-            desc.d_line_lu[a] = self.d_line_lu[a].data_ptr()
-            desc.n_unique[a] = self.d_line_lu[a].shape[0]
+            ax = desc.axis[a]
+            ax.d_line_id = self.d_line_id[a].data_ptr()
+            ax.n_unique = self.d_line_lu[a].shape[0]
+            ax.d_lu = self.d_line_lu[a].data_ptr()
+            ax.chunk, ax.n_chunks = self.chunk[a]
+            if self.d_chunk[a] is not None:
+                ax.d_tab, ax.d_GE = (t.data_ptr() for t in self.d_chunk[a])
+                ax.pitch = self.d_chunk[a][0].shape[2]
         desc.device = dev.index
+        desc.flags = self.flags
         handle = ctypes.c_void_p()
         with torch.cuda.device(dev):
             _cabi.check(lib.hs2_plan_create(ctypes.byref(desc), ctypes.byref(handle)))

@@ -46,6 +46,34 @@ extern "C" {
  * there, 32 B per row of a *unique* line here.                              */
 #define HS2_LU_STRIDE 4
 
+/* Partitioned (SPIKE-type) solve: a line of length L is cut into n_chunks
+ * chunks of `chunk` rows (last one may be shorter); each chunk is eliminated
+ * independently and the chunk interfaces are recovered from a precomputed
+ * dense operator.  Tables per unique line (heatsim2_b200/plan.py,
+ * chunk_factors, documents the algebra):
+ *   d_tab [n_unique][HS2_T_PLANES][pitch]  planes 1/piv, lo/piv, c, s, hi/piv
+ *                                          (chunk-local factorisation)
+ *   d_GE  [n_unique][n_chunks][2*n_chunks] row of the inverse interface
+ *                                          operator giving the chunk's last x
+ * chunk == 0 means the tables are absent and the whole-line path is used.   */
+#define HS2_T_INV 0
+#define HS2_T_F 1
+#define HS2_T_C 2
+#define HS2_T_S 3
+#define HS2_T_CP 4
+#define HS2_T_PLANES 5
+
+typedef struct hs2_axis_tables {
+  const uint32_t *d_line_id; /* device [n_lines]: unique-line id of each line  */
+  const double *d_lu;        /* device [n_unique][L][HS2_LU_STRIDE]            */
+  const double *d_tab;
+  const double *d_GE;
+  int32_t n_unique;
+  int32_t chunk;
+  int32_t n_chunks;
+  int32_t pitch;             /* doubles per table plane (even, >= L)           */
+} hs2_axis_tables;
+
 /* Axis numbering used by every per-axis array: 0 = x (contiguous), 1 = y,
  * 2 = z (slowest).  Line numbering: x-lines k*ny+j, y-lines k*nx+i,
  * z-lines j*nx+i.                                                            */
@@ -55,11 +83,12 @@ typedef struct hs2_plan_desc {
   int32_t class_id_bytes;      /* 1 (u8) or 2 (u16)                           */
   const void *d_class_id;      /* device, [nz][ny][nx]                        */
   const double *d_class_coef;  /* device, [n_classes][HS2_COEF_STRIDE]        */
-  const uint32_t *d_line_id[3];/* device, unique-line id of every line        */
-  const double *d_line_lu[3];  /* device, [n_unique][L_axis][HS2_LU_STRIDE]   */
-  int32_t n_unique[3];
+  hs2_axis_tables axis[3];
   int32_t device;              /* CUDA device ordinal the buffers live on     */
+  int32_t flags;               /* HS2_FLAG_*                                  */
 } hs2_plan_desc;
+
+#define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
 
 typedef struct hs2_plan hs2_plan;
 
@@ -83,6 +112,8 @@ const char *hs2_last_error(void);
 int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out);
 /* replaces delete_adi_step (alternatingdirection_c.h:50)                      */
 int hs2_plan_destroy(hs2_plan *plan);
+/* number of kernels one hs2_step launches with this plan                     */
+int hs2_plan_launches_per_step(const hs2_plan *plan);
 
 /* One ADI time step = run_adi_steps (alternatingdirection_c_pyx.pyx:287-416).
  *   d_T_in   [nz][ny][nx]  field at t - dt/2

@@ -17,7 +17,7 @@ def test_library_exports_header_symbols():
     build.build()
     L = _cabi.lib()
     names = _declared()
-    assert len(names) >= 11
+    assert len(names) >= 12
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_cabi.PROTOTYPES) == names
@@ -27,8 +27,9 @@ def test_library_exports_header_symbols():
 def test_struct_layout_matches_header():
     import ctypes
     from heatsim2_b200 import _cabi
-    # int64 x3, int32 x2, ptr x2, ptr[3] x2, int32[3], int32  -> 8-byte aligned
-    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 48 + 12 + 4
+    # axis tables: 5 pointers + 4 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x2
+    assert ctypes.sizeof(_cabi.AxisTables) == 32 + 16
+    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 48 + 8
     assert ctypes.sizeof(_cabi.Source) == 24
 
 

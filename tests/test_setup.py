@@ -224,3 +224,62 @@ def test_no_cuda_means_loud_failure():
     P, S = hs.setup(*prob["setup_args"])
     with pytest.raises(RuntimeError, match="no CPU"):
         hs.run_adi_steps(P, S, 0.0, prob["dt"], prob["T0"], prob["volumetric_elements"], prob["volumetric"])
+
+
+def _emulate_chunk_kernel(tab, GE, M, d):
+    """numpy transcription of csrc/kernels_strided.cu (one line)."""
+    from heatsim2_b200.plan import T_INV, T_F, T_C, T_S, T_CP
+    L = len(d)
+    P = -(-L // M)
+    u = np.zeros(L)
+    Y = np.zeros(2 * P)
+    for p in range(P):
+        prev, acc = 0.0, 0.0
+        for r in range(p * M, min(L, (p + 1) * M)):
+            prev = d[r] * tab[T_INV, r] - tab[T_F, r] * prev
+            u[r] = prev
+            acc += tab[T_C, r] * prev
+        Y[2 * p], Y[2 * p + 1] = acc, prev
+    E = GE @ Y
+    x = np.zeros(L)
+    for p in range(P):
+        alpha = E[p - 1] if p > 0 else 0.0
+        r1 = min(L, (p + 1) * M)
+        nxt = E[p]
+        x[r1 - 1] = nxt
+        for r in range(r1 - 2, p * M - 1, -1):
+            nxt = (u[r] - alpha * tab[T_S, r]) - tab[T_CP, r] * nxt
+            x[r] = nxt
+    return x
+
+
+@pytest.mark.parametrize("L", [1, 2, 5, 40, 64, 100, 257, 512, 1000])
+def test_chunk_tables_solve_lines(L):
+    from heatsim2_b200.plan import chunk_factors, choose_chunk
+    rng = np.random.default_rng(L)
+    nu = 3
+    lo = -6 * rng.random((nu, L))
+    hi = -6 * rng.random((nu, L))
+    lo[:, 0] = 0
+    hi[:, -1] = 0
+    lo[1, L // 2] = 0                       # a FIXED-like break
+    hi[2, L // 3] = 0
+    dg = 1 - lo - hi
+    M, P = choose_chunk(L)
+    assert M in (8, 16, 32) and P == -(-L // M)
+    tab, GE = chunk_factors(lo, dg, hi, M)
+    assert tab.shape[2] % 2 == 0 and tab.shape[2] >= L
+    for u in range(nu):
+        A = np.diag(dg[u]) + np.diag(lo[u, 1:], -1) + np.diag(hi[u, :-1], 1)
+        d = rng.random(L)
+        x = _emulate_chunk_kernel(tab[u], GE[u], M, d)
+        assert util.relerr(x, np.linalg.solve(A, d)) < 1e-13
+
+
+def test_choose_chunk_limits():
+    from heatsim2_b200.plan import choose_chunk
+    assert choose_chunk(48) == (8, 6)
+    assert choose_chunk(256) == (16, 16)
+    assert choose_chunk(512) in ((16, 32), (32, 16))
+    assert choose_chunk(1024) == (32, 32)
+    assert choose_chunk(1025) == (0, 0)
