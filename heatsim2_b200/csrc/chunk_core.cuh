@@ -1,0 +1,119 @@
+// chunk_core.cuh - per-thread arithmetic of the partitioned tridiagonal solve,
+// shared by the strided (y, z) and the contiguous (x) sweep kernels.
+//
+// A thread owns M consecutive rows of one line in registers.  Tables (one set
+// per unique line, planes of `pitch` doubles, see heatsim2_b200/plan.py
+// chunk_factors): INV, F, C for the forward part, S, CP for the backward part.
+// `tb` points at the chunk's first row inside plane 0.
+#pragma once
+#include "hs2_common.cuh"
+
+// forward elimination of a full chunk; returns the first-row functional yf
+// and leaves the chunk's local forward solution in v (v[M-1] is y_last)
+template <int M>
+__device__ __forceinline__ double chunk_forward_full(double (&v)[M], const double *__restrict__ tb, int pitch) {
+  {
+    const double2 *ci = reinterpret_cast<const double2 *>(tb + HS2_T_INV * pitch);
+#pragma unroll
+    for (int t = 0; t < M; t += 2) {
+      const double2 c = __ldg(ci + t / 2);
+      v[t] *= c.x;
+      v[t + 1] *= c.y;
+    }
+  }
+  {
+    const double2 *cf = reinterpret_cast<const double2 *>(tb + HS2_T_F * pitch);
+    double prev = 0.0;
+#pragma unroll
+    for (int t = 0; t < M; t += 2) {
+      const double2 c = __ldg(cf + t / 2);
+      prev = fma(-c.x, prev, v[t]);
+      v[t] = prev;
+      prev = fma(-c.y, prev, v[t + 1]);
+      v[t + 1] = prev;
+    }
+  }
+  const double2 *cc = reinterpret_cast<const double2 *>(tb + HS2_T_C * pitch);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int t = 0; t < M; t += 2) {
+    const double2 c = __ldg(cc + t / 2);
+    a0 = fma(c.x, v[t], a0);
+    a1 = fma(c.y, v[t + 1], a1);
+  }
+  return a0 + a1;
+}
+
+// same for a chunk of `rows` < M rows (last chunk of a line); *last = y_last
+template <int M>
+__device__ __forceinline__ double chunk_forward_short(double (&v)[M], const double *__restrict__ tb, int pitch, int rows,
+                                                      double *last) {
+  double prev = 0.0, yf = 0.0;
+#pragma unroll
+  for (int t = 0; t < M; ++t) {
+    if (t < rows) {
+      prev = fma(-__ldg(tb + HS2_T_F * pitch + t), prev, v[t] * __ldg(tb + HS2_T_INV * pitch + t));
+      v[t] = prev;
+      yf = fma(__ldg(tb + HS2_T_C * pitch + t), prev, yf);
+    }
+  }
+  *last = prev;
+  return yf;
+}
+
+// back substitution given alpha (true x just before the chunk) and E (true x
+// of the chunk's last row); v becomes the solution
+template <int M>
+__device__ __forceinline__ void chunk_backward_full(double (&v)[M], const double *__restrict__ tb, int pitch, double alpha,
+                                                    double E) {
+  {
+    const double2 *cs = reinterpret_cast<const double2 *>(tb + HS2_T_S * pitch);
+#pragma unroll
+    for (int t = 0; t < M; t += 2) {
+      const double2 c = __ldg(cs + t / 2);
+      v[t] = fma(-alpha, c.x, v[t]);
+      v[t + 1] = fma(-alpha, c.y, v[t + 1]);
+    }
+  }
+  const double2 *cp = reinterpret_cast<const double2 *>(tb + HS2_T_CP * pitch);
+  double nxt = E;
+  v[M - 1] = E;
+#pragma unroll
+  for (int t = M - 2; t >= 0; t -= 2) {
+    const double2 c = __ldg(cp + t / 2);  // (cp[t], cp[t+1])
+    if (t + 1 < M - 1) {
+      nxt = fma(-c.y, nxt, v[t + 1]);
+      v[t + 1] = nxt;
+    }
+    nxt = fma(-c.x, nxt, v[t]);
+    v[t] = nxt;
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void chunk_backward_short(double (&v)[M], const double *__restrict__ tb, int pitch, int rows,
+                                                     double alpha, double E) {
+  double nxt = E;
+#pragma unroll
+  for (int t = M - 1; t >= 0; --t) {
+    if (t < rows) {
+      if (t < rows - 1)
+        nxt = fma(-__ldg(tb + HS2_T_CP * pitch + t), nxt, fma(-alpha, __ldg(tb + HS2_T_S * pitch + t), v[t]));
+      v[t] = nxt;
+    }
+  }
+}
+
+// E_p = row p of the inverse interface operator applied to the interleaved
+// (yf_0, yl_0, yf_1, yl_1, ...) values of this line held in Y[2P][ld] column w
+__device__ __forceinline__ double chunk_interface(const double *__restrict__ ge, const double *Y, int P, int ld, int w) {
+  double e0 = 0.0, e1 = 0.0;
+  const double2 *g2 = reinterpret_cast<const double2 *>(ge);
+#pragma unroll 4
+  for (int q = 0; q < P; ++q) {
+    const double2 g = __ldg(g2 + q);
+    e0 = fma(g.x, Y[(2 * q) * ld + w], e0);
+    e1 = fma(g.y, Y[(2 * q + 1) * ld + w], e1);
+  }
+  return e0 + e1;
+}

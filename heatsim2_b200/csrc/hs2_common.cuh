@@ -44,3 +44,6 @@ int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaSt
 bool hs2_tile_supported(const hs2_plan *p, int axis);
 int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
+bool hs2_tile_x_supported(const hs2_plan *p);
+int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
+                     const double *halo_hi, cudaStream_t st);

@@ -19,7 +19,7 @@
 // only serial part (one DFMA per row per direction).
 // This replaces heatsim2/tridiag.pyx:46-69 (one serial chain over the whole
 // grid) and the transposes of alternatingdirection_c_pyx.pyx:397,412.
-#include "hs2_common.cuh"
+#include "chunk_core.cuh"
 
 namespace {
 
@@ -45,6 +45,7 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
   const int64_t base = (int64_t)group * group_stride + (live ? col : 0);
   const int r0 = p * M;
   const int rows = min(M, L - r0);       // >= 1 for every launched chunk
+  const bool full = rows == M;
   const uint32_t lid = line_id[line];
   const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
   const double *ge = GE + ((int64_t)lid * P + p) * (2 * P);
@@ -52,109 +53,29 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
 
   double v[M];
   double yf, last;
-  if (rows == M) {
-    // ---------------------------------------------------------- full chunk
-    {
-      const double *src = data + off;
-#pragma unroll
-      for (int t = 0; t < M; ++t) {
-        v[t] = live ? *src : 0.0;
-        src += stride;
-      }
-    }
-    {
-      const double2 *ci = reinterpret_cast<const double2 *>(tb + HS2_T_INV * pitch);
-#pragma unroll
-      for (int t = 0; t < M; t += 2) {
-        const double2 c = __ldg(ci + t / 2);
-        v[t] *= c.x;
-        v[t + 1] *= c.y;
-      }
-    }
-    {
-      const double2 *cf = reinterpret_cast<const double2 *>(tb + HS2_T_F * pitch);
-      double prev = 0.0;
-#pragma unroll
-      for (int t = 0; t < M; t += 2) {
-        const double2 c = __ldg(cf + t / 2);
-        prev = fma(-c.x, prev, v[t]);
-        v[t] = prev;
-        prev = fma(-c.y, prev, v[t + 1]);
-        v[t + 1] = prev;
-      }
-      last = prev;
-    }
-    {
-      const double2 *cc = reinterpret_cast<const double2 *>(tb + HS2_T_C * pitch);
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int t = 0; t < M; t += 2) {
-        const double2 c = __ldg(cc + t / 2);
-        a0 = fma(c.x, v[t], a0);
-        a1 = fma(c.y, v[t + 1], a1);
-      }
-      yf = a0 + a1;
-    }
-  } else {
-    // ------------------------------------------- short last chunk (generic)
-    double prev = 0.0;
-    yf = 0.0;
+  if (full) {
+    const double *src = data + off;
 #pragma unroll
     for (int t = 0; t < M; ++t) {
-      v[t] = 0.0;
-      if (t < rows) {
-        const double d = live ? data[off + (int64_t)t * stride] : 0.0;
-        prev = fma(-__ldg(tb + HS2_T_F * pitch + t), prev, d * __ldg(tb + HS2_T_INV * pitch + t));
-        v[t] = prev;
-        yf = fma(__ldg(tb + HS2_T_C * pitch + t), prev, yf);
-      }
+      v[t] = live ? *src : 0.0;
+      src += stride;
     }
-    last = prev;
+    yf = chunk_forward_full<M>(v, tb, pitch);
+    last = v[M - 1];
+  } else {
+#pragma unroll
+    for (int t = 0; t < M; ++t) v[t] = (live && t < rows) ? data[off + (int64_t)t * stride] : 0.0;
+    yf = chunk_forward_short<M>(v, tb, pitch, rows, &last);
   }
   Y[(2 * p) * W + w] = yf;
   Y[(2 * p + 1) * W + w] = last;
   __syncthreads();
-  // true value of this chunk's last row from the inverse of the interface system
-  double E;
-  {
-    double e0 = 0.0, e1 = 0.0;
-    const double2 *g2 = reinterpret_cast<const double2 *>(ge);
-#pragma unroll 4
-    for (int q = 0; q < P; ++q) {
-      const double2 g = __ldg(g2 + q);           // weights of (yf_q, yl_q)
-      e0 = fma(g.x, Y[(2 * q) * W + w], e0);
-      e1 = fma(g.y, Y[(2 * q + 1) * W + w], e1);
-    }
-    E = e0 + e1;
-  }
+  const double E = chunk_interface(ge, Y, P, W, w);
   Es[p * W + w] = E;
   __syncthreads();
   const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
-  if (rows == M) {
-    {
-      const double2 *cs = reinterpret_cast<const double2 *>(tb + HS2_T_S * pitch);
-#pragma unroll
-      for (int t = 0; t < M; t += 2) {
-        const double2 c = __ldg(cs + t / 2);
-        v[t] = fma(-alpha, c.x, v[t]);
-        v[t + 1] = fma(-alpha, c.y, v[t + 1]);
-      }
-    }
-    {
-      const double2 *cp = reinterpret_cast<const double2 *>(tb + HS2_T_CP * pitch);
-      double nxt = E;
-      v[M - 1] = E;
-#pragma unroll
-      for (int t = M - 2; t >= 0; t -= 2) {
-        const double2 c = __ldg(cp + t / 2);           // (cp[t], cp[t+1])
-        if (t + 1 < M - 1) {
-          nxt = fma(-c.y, nxt, v[t + 1]);
-          v[t + 1] = nxt;
-        }
-        nxt = fma(-c.x, nxt, v[t]);
-        v[t] = nxt;
-      }
-    }
+  if (full) {
+    chunk_backward_full<M>(v, tb, pitch, alpha, E);
     if (live) {
       if (FINAL) {
         const double *ti = Tin + off;
@@ -175,18 +96,16 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
       }
     }
   } else {
-    double nxt = E;
+    chunk_backward_short<M>(v, tb, pitch, rows, alpha, E);
+    if (live) {
 #pragma unroll
-    for (int t = M - 1; t >= 0; --t) {
-      if (t < rows) {
-        if (t < rows - 1)
-          nxt = fma(-__ldg(tb + HS2_T_CP * pitch + t), nxt, fma(-alpha, __ldg(tb + HS2_T_S * pitch + t), v[t]));
-        if (live) {
+      for (int t = 0; t < M; ++t) {
+        if (t < rows) {
           const int64_t a = off + (int64_t)t * stride;
           if (FINAL)
-            Tout[a] = Tin[a] + nxt;
+            Tout[a] = Tin[a] + v[t];
           else
-            data[a] = nxt;
+            data[a] = v[t];
         }
       }
     }

@@ -1,0 +1,243 @@
+// kernels_x.cu - stage 0 of the ADI step in one kernel: explicit 7-point right
+// hand side + implicit solve along the contiguous axis.
+//   d1 = (I - 1/2 M^-1 Lx)^-1  M^-1 [ (Lx + Ly + Lz) T + D s ]
+// Replaces B0.dot(T) + Dvec*src + tridiagsolve of stage 0
+// (heatsim2/alternatingdirection_c_pyx.pyx:397-412): neither the CSR matrix nor
+// the right hand side ever exist in HBM.  HBM traffic per cell: read T once
+// (y/z neighbours are re-reads served by L1/L2), write d1 once, + 1-2 B class id.
+//
+// A block owns R consecutive x-lines (rows j0..j0+R-1 of plane k).
+//  phase 1  all threads walk the tile column-wise (coalesced along x), keep the
+//           y-window (j-1, j, j+1) in registers, fetch the z neighbours from
+//           global memory and write the right hand side into shared memory in
+//           a chunk-padded layout;
+//  phase 2  thread (r, p) takes chunk p (M consecutive cells) of line r into
+//           registers and runs the partitioned tridiagonal solve of
+//           chunk_core.cuh (lanes of a warp = different lines, so the per-row
+//           factors are warp-uniform loads);
+//  phase 3  the solution goes back through shared memory and is stored
+//           coalesced.
+// Shared-memory layout: cell (r, i) at r*S_r + i + i/M doubles - one pad word
+// per chunk and S_r = 2 mod 16 make both the row-major phases and the
+// chunk-major phase bank-conflict free for 8-byte accesses.
+#include "chunk_core.cuh"
+
+namespace {
+
+constexpr int R = 8;  // lines per block
+
+struct SrcTab {
+  int n;
+  uint8_t idx[8];
+  double val[8];
+};
+
+__host__ __device__ inline int row_pitch(int P, int M) {
+  int s = P * (M + 1);
+  while ((s & 15) != 2) ++s;
+  return s;
+}
+
+template <int M, typename CID>
+__global__ void __launch_bounds__(256, 2)
+sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CID *__restrict__ cid,
+               const double *__restrict__ coef_g, int n_classes, int coef_in_smem,
+               const uint8_t *__restrict__ vol, SrcTab st, const double *__restrict__ dense,
+               const double *__restrict__ halo_lo, const double *__restrict__ halo_hi,
+               const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
+               int nz, int ny, int nx, int pitch, int P, int tiles_y) {
+  extern __shared__ double sm[];
+  const int Sr = row_pitch(P, M);
+  double *buf = sm;                       // [R][Sr]
+  double *Y = buf + R * Sr;               // [2P][R]
+  double *Es = Y + 2 * P * R;             // [P][R]
+  double *cfs = Es + P * R;               // [n_classes][8] when coef_in_smem
+  const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;
+  const int k = blockIdx.x / tiles_y;
+  const int j0 = (blockIdx.x % tiles_y) * R;
+  const int64_t plane = (int64_t)ny * nx;
+  const int64_t kbase = (int64_t)k * plane;
+
+  if (coef_in_smem) {
+    for (int q = tid; q < n_classes * HS2_COEF_STRIDE; q += nthreads) cfs[q] = coef_g[q];
+    __syncthreads();
+  }
+  const double *coef = coef_in_smem ? cfs : coef_g;
+  const int nrows = min(R, ny - j0);
+
+  // ------------------------------------------------ phase 1: right hand side
+  for (int i = tid; i < nx; i += nthreads) {
+    const int im = i > 0 ? i - 1 : 0;
+    const int ip = i < nx - 1 ? i + 1 : nx - 1;
+    const int so = i + i / M;
+    const int jm = j0 > 0 ? j0 - 1 : 0;
+    double tm = T[kbase + (int64_t)jm * nx + i];
+    double tc = T[kbase + (int64_t)j0 * nx + i];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r < nrows) {
+        const int j = j0 + r;
+        const int64_t rowb = kbase + (int64_t)j * nx;
+        const int jp = j < ny - 1 ? j + 1 : j;
+        const double tp = T[kbase + (int64_t)jp * nx + i];
+        const double xm = T[rowb + im];
+        const double xp = T[rowb + ip];
+        const int64_t idx = rowb + i;
+        double zm, zp;
+        if (k > 0)
+          zm = T[idx - plane];
+        else
+          zm = halo_lo ? halo_lo[(int64_t)j * nx + i] : tc;
+        if (k < nz - 1)
+          zp = T[idx + plane];
+        else
+          zp = halo_hi ? halo_hi[(int64_t)j * nx + i] : tc;
+        const double2 *c2 = reinterpret_cast<const double2 *>(coef + (int)cid[idx] * HS2_COEF_STRIDE);
+        const double2 cx = c2[0], cy = c2[1], cz = c2[2], cs = c2[3];
+        double rr = cx.x * (xm - tc);
+        rr = fma(cx.y, xp - tc, rr);
+        rr = fma(cy.x, tm - tc, rr);
+        rr = fma(cy.y, tp - tc, rr);
+        rr = fma(cz.x, zm - tc, rr);
+        rr = fma(cz.y, zp - tc, rr);
+        if (dense || st.n) {
+          double s = dense ? dense[idx] : 0.0;
+          if (st.n) {
+            const uint8_t vv = vol[idx];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < st.n && st.idx[q] == vv) s += st.val[q];
+          }
+          rr = fma(cs.x, s, rr);
+        }
+        buf[r * Sr + so] = rr;
+        tm = tc;
+        tc = tp;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------ phase 2: solve along x
+  const int r = tid % R;
+  const int p = tid / R;
+  const bool live = r < nrows && p < P;
+  const int pc = p < P ? p : P - 1;
+  const int c0 = pc * M;
+  const int rows = min(M, nx - c0);
+  const bool full = rows == M;
+  const int64_t line = (int64_t)k * ny + j0 + (r < nrows ? r : 0);
+  const uint32_t lid = line_id[line];
+  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + c0;
+  const double *ge = GE + ((int64_t)lid * P + pc) * (2 * P);
+  double *mine = buf + r * Sr + pc * (M + 1);
+  double v[M];
+  double yf, last;
+  if (full) {
+#pragma unroll
+    for (int t = 0; t < M; ++t) v[t] = mine[t];
+    yf = chunk_forward_full<M>(v, tb, pitch);
+    last = v[M - 1];
+  } else {
+#pragma unroll
+    for (int t = 0; t < M; ++t) v[t] = t < rows ? mine[t] : 0.0;
+    yf = chunk_forward_short<M>(v, tb, pitch, rows, &last);
+  }
+  if (p < P) {
+    Y[(2 * p) * R + r] = yf;
+    Y[(2 * p + 1) * R + r] = last;
+  }
+  __syncthreads();
+  const double E = chunk_interface(ge, Y, P, R, r);
+  if (p < P) Es[p * R + r] = E;
+  __syncthreads();
+  const double alpha = (p > 0 && p < P) ? Es[(p - 1) * R + r] : 0.0;
+  if (full)
+    chunk_backward_full<M>(v, tb, pitch, alpha, E);
+  else
+    chunk_backward_short<M>(v, tb, pitch, rows, alpha, E);
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < M; ++t)
+      if (t < rows) mine[t] = v[t];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------ phase 3: coalesced store
+  for (int rr = 0; rr < nrows; ++rr) {
+    double *dst = Wout + kbase + (int64_t)(j0 + rr) * nx;
+    const double *srow = buf + rr * Sr;
+    for (int i = tid; i < nx; i += nthreads) dst[i] = srow[i + i / M];
+  }
+}
+
+int make_src_tab(const hs2_source *src, SrcTab *st) {
+  st->n = 0;
+  if (!src || !src->h_value || !src->d_vol_elements) return HS2_OK;
+  for (int v = 0; v < 256; ++v) {
+    if (src->h_value[v] != 0.0) {
+      HS2_REQUIRE(st->n < 8, "hs2_source: more than 8 active volumetric classes in one step; pass a dense source array instead");
+      st->idx[st->n] = (uint8_t)v;
+      st->val[st->n] = src->h_value[v];
+      st->n++;
+    }
+  }
+  return HS2_OK;
+}
+
+template <int M, typename CID>
+int launch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const SrcTab &tabsrc, const double *halo_lo,
+             const double *halo_hi, cudaStream_t st) {
+  const hs2_plan_desc &d = p->d;
+  const hs2_axis_tables &ax = d.axis[0];
+  const int P = ax.n_chunks;
+  const int threads = R * P;
+  const int Sr = row_pitch(P, M);
+  const int coef_in_smem = d.n_classes <= 256 ? 1 : 0;
+  const size_t smem = ((size_t)R * Sr + 3 * (size_t)P * R + (coef_in_smem ? (size_t)d.n_classes * HS2_COEF_STRIDE : 0)) *
+                      sizeof(double);
+  HS2_REQUIRE(smem <= (size_t)p->max_smem_optin, "x sweep: tile needs %zu B of shared memory", smem);
+  auto kern = sweep_x_kernel<M, CID>;
+  if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles_y = (int)((d.ny + R - 1) / R);
+  const int64_t blocks = d.nz * tiles_y;
+  HS2_REQUIRE(blocks < ((int64_t)1 << 31), "x sweep: too many tiles");
+  const uint8_t *vol = (src && tabsrc.n) ? src->d_vol_elements : nullptr;
+  const double *dense = src ? src->d_dense : nullptr;
+  kern<<<(unsigned)blocks, threads, smem, st>>>(T, W, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes, coef_in_smem,
+                                                 vol, tabsrc, dense, halo_lo, halo_hi, ax.d_line_id, ax.d_tab, ax.d_GE,
+                                                 (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, tiles_y);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  return HS2_OK;
+}
+
+template <typename CID>
+int dispatch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const SrcTab &tabsrc,
+               const double *halo_lo, const double *halo_hi, cudaStream_t st) {
+  switch (p->d.axis[0].chunk) {
+    case 8: return launch_x<8, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+    case 16: return launch_x<16, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+    case 32: return launch_x<32, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+  }
+  hs2_set_error("x sweep: unsupported chunk size %d", p->d.axis[0].chunk);
+  return HS2_E_INVALID;
+}
+
+}  // namespace
+
+bool hs2_tile_x_supported(const hs2_plan *p) {
+  if (!hs2_tile_supported(p, 0)) return false;
+  const hs2_plan_desc &d = p->d;
+  if (d.nx >= ((int64_t)1 << 30) || d.ny >= ((int64_t)1 << 30) || d.nz >= ((int64_t)1 << 30)) return false;
+  return d.axis[0].n_chunks * R <= 256;
+}
+
+int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
+                     const double *halo_hi, cudaStream_t st) {
+  SrcTab tabsrc;
+  int rc = make_src_tab(src, &tabsrc);
+  if (rc) return rc;
+  if (p->d.class_id_bytes == 1) return dispatch_x<uint8_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+  return dispatch_x<uint16_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+}

@@ -59,13 +59,13 @@ def choose_chunk(L):
     hold M doubles per thread in registers and run P*W threads per tile
     (W = 16 or 8 adjacent lines): M=8 with up to 16 chunks, M=16 with up to 32,
     M=32 with up to 32.  The smallest valid M is taken, except that lines
-    longer than 256 rows use HS2_CHUNK (default 16) when it is valid.
+    longer than 256 rows use HS2_CHUNK (default 32) when it is valid.
     (0, 0): too long for the register-tile kernels (whole-line fallback)."""
     valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
     if not valid:
         return 0, 0
     if L > 256:
-        pref = int(os.environ.get("HS2_CHUNK", "16"))
+        pref = int(os.environ.get("HS2_CHUNK", "32"))
         for M, P in valid:
             if M == pref:
                 return M, P
