@@ -67,54 +67,59 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   const int nrows = min(R, ny - j0);
 
   // ------------------------------------------------ phase 1: right hand side
+  // z neighbours: the planes below/above, the neighbouring slab's halo plane,
+  // or (domain face, conductance 0) the cell itself
+  const double *zlo = k > 0 ? T + kbase - plane : (halo_lo ? halo_lo : T + kbase);
+  const double *zhi = k < nz - 1 ? T + kbase + plane : (halo_hi ? halo_hi : T + kbase);
+  const double *Tk = T + kbase;
+  const CID *cidk = cid + kbase;
+  const bool has_src = dense != nullptr || st.n > 0;
   for (int i = tid; i < nx; i += nthreads) {
     const int im = i > 0 ? i - 1 : 0;
     const int ip = i < nx - 1 ? i + 1 : nx - 1;
-    const int so = i + i / M;
-    const int jm = j0 > 0 ? j0 - 1 : 0;
-    double tm = T[kbase + (int64_t)jm * nx + i];
-    double tc = T[kbase + (int64_t)j0 * nx + i];
+    double tcol[R + 2], xm[R], xp[R], zm[R], zp[R];
+    int id[R];
+    // issue every load of the column strip before any arithmetic
+#pragma unroll
+    for (int r = -1; r <= R; ++r) {
+      int j = j0 + r;
+      j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
+      tcol[r + 1] = Tk[(int64_t)j * nx + i];
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (r < nrows) {
-        const int j = j0 + r;
-        const int64_t rowb = kbase + (int64_t)j * nx;
-        const int jp = j < ny - 1 ? j + 1 : j;
-        const double tp = T[kbase + (int64_t)jp * nx + i];
-        const double xm = T[rowb + im];
-        const double xp = T[rowb + ip];
-        const int64_t idx = rowb + i;
-        double zm, zp;
-        if (k > 0)
-          zm = T[idx - plane];
-        else
-          zm = halo_lo ? halo_lo[(int64_t)j * nx + i] : tc;
-        if (k < nz - 1)
-          zp = T[idx + plane];
-        else
-          zp = halo_hi ? halo_hi[(int64_t)j * nx + i] : tc;
-        const double2 *c2 = reinterpret_cast<const double2 *>(coef + (int)cid[idx] * HS2_COEF_STRIDE);
-        const double2 cx = c2[0], cy = c2[1], cz = c2[2], cs = c2[3];
-        double rr = cx.x * (xm - tc);
-        rr = fma(cx.y, xp - tc, rr);
-        rr = fma(cy.x, tm - tc, rr);
-        rr = fma(cy.y, tp - tc, rr);
-        rr = fma(cz.x, zm - tc, rr);
-        rr = fma(cz.y, zp - tc, rr);
-        if (dense || st.n) {
-          double s = dense ? dense[idx] : 0.0;
-          if (st.n) {
-            const uint8_t vv = vol[idx];
+      const int j = min(j0 + r, ny - 1);
+      const int64_t rowo = (int64_t)j * nx;
+      xm[r] = Tk[rowo + im];
+      xp[r] = Tk[rowo + ip];
+      zm[r] = zlo[rowo + i];
+      zp[r] = zhi[rowo + i];
+      id[r] = (int)cidk[rowo + i];
+    }
+    double *bcol = buf + i + i / M;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q < st.n && st.idx[q] == vv) s += st.val[q];
-          }
-          rr = fma(cs.x, s, rr);
+    for (int r = 0; r < R; ++r) {
+      const double tc = tcol[r + 1];
+      const double2 *c2 = reinterpret_cast<const double2 *>(coef + id[r] * HS2_COEF_STRIDE);
+      const double2 cx = c2[0], cy = c2[1], cz = c2[2];
+      double rr = cx.x * (xm[r] - tc);
+      rr = fma(cx.y, xp[r] - tc, rr);
+      rr = fma(cy.x, tcol[r] - tc, rr);
+      rr = fma(cy.y, tcol[r + 2] - tc, rr);
+      rr = fma(cz.x, zm[r] - tc, rr);
+      rr = fma(cz.y, zp[r] - tc, rr);
+      if (has_src && r < nrows) {
+        const int64_t idx = kbase + (int64_t)(j0 + r) * nx + i;
+        double s = dense ? dense[idx] : 0.0;
+        if (st.n) {
+          const uint8_t vv = vol[idx];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < st.n && st.idx[q] == vv) s += st.val[q];
         }
-        buf[r * Sr + so] = rr;
-        tm = tc;
-        tc = tp;
+        rr = fma(c2[3].x, s, rr);
       }
+      bcol[r * Sr] = rr;
     }
   }
   __syncthreads();
@@ -165,10 +170,15 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   __syncthreads();
 
   // ------------------------------------------------ phase 3: coalesced store
-  for (int rr = 0; rr < nrows; ++rr) {
-    double *dst = Wout + kbase + (int64_t)(j0 + rr) * nx;
-    const double *srow = buf + rr * Sr;
-    for (int i = tid; i < nx; i += nthreads) dst[i] = srow[i + i / M];
+  double *Wk = Wout + kbase + (int64_t)j0 * nx;
+  for (int i = tid; i < nx; i += nthreads) {
+    const double *bcol = buf + i + i / M;
+    double o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) o[r] = bcol[r * Sr];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (r < nrows) Wk[(int64_t)r * nx + i] = o[r];
   }
 }
 
