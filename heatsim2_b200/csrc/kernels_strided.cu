@@ -20,6 +20,8 @@
 // This replaces heatsim2/tridiag.pyx:46-69 (one serial chain over the whole
 // grid) and the transposes of alternatingdirection_c_pyx.pyx:397,412.
 #include "chunk_core.cuh"
+#include "tma_util.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -112,6 +114,161 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
   }
 }
 
+// Persistent variant: a block walks tiles blockIdx.x, +gridDim.x, ...; the
+// next tile is fetched into shared memory by the TMA engine
+// (cp.async.bulk.tensor) while the current one is being solved from registers,
+// so HBM reads never wait for arithmetic.  The tile lands as dense rows
+// [L_pad][W]; thread (w, p) copies its chunk to registers, after which the
+// buffer is handed back to the copy engine.  Results are stored straight from
+// registers.  Tensor map: rank 3, dims (n0, n1, n2) = (nx, ny, nz) for the
+// y-sweep and (ny*nx, nz, 1) for the z-sweep, box (W, BR, 1).
+template <int M, int W, bool FINAL>
+__global__ void __launch_bounds__(256, 2)
+strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__ data, const double *__restrict__ Tin,
+                  double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
+                  const double *__restrict__ GE, int L, int pitch, int P, int64_t stride, int tiles_per_group,
+                  int lines_per_group, int64_t group_stride, int n_tiles, int BR, int n_boxes, int do_prefetch) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *tile = reinterpret_cast<double *>(smraw);              // [n_boxes*BR][W]
+  double *Y = tile + (size_t)n_boxes * BR * W;                     // [2P][W]
+  double *Es = Y + 2 * P * W;                                      // [P][W]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(Es + P * W);
+  const int w = threadIdx.x;
+  const int p = threadIdx.y;
+  const bool leader = (w == 0 && p == 0);
+  const int r0 = p * M;
+  const int rows = min(M, L - r0);
+  const bool full = rows == M;
+  const uint32_t tile_bytes = (uint32_t)n_boxes * BR * W * sizeof(double);
+
+  if (leader) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int group = t / tiles_per_group;
+    const int c0 = (t % tiles_per_group) * W;
+    mbar_expect_tx(bar, tile_bytes);
+    for (int b = 0; b < n_boxes; ++b) {
+      if (group_stride)   // y-sweep: (x, row, plane)
+        tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, group);
+      else                // z-sweep: (flattened line, row, 0)
+        tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, 0);
+    }
+  };
+  int t = blockIdx.x;
+  if (leader && t < n_tiles) issue(t);
+  uint32_t parity = 0;
+  for (; t < n_tiles; t += gridDim.x) {
+    const int group = t / tiles_per_group;
+    const int col = (t % tiles_per_group) * W + w;
+    const bool live = col < lines_per_group;
+    const int64_t line = (int64_t)group * lines_per_group + (live ? col : 0);
+    const int64_t off = (int64_t)group * group_stride + (live ? col : 0) + (int64_t)r0 * stride;
+    const uint32_t lid = line_id[line];
+    const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
+    const double *ge = GE + ((int64_t)lid * P + p) * (2 * P);
+    if (FINAL && live && do_prefetch) {
+      // warm L2 with the T_in rows this thread adds at the end
+      const double *ti = Tin + off;
+#pragma unroll
+      for (int q = 0; q < M; q += 4)
+        if (q < rows) prefetch_l2(ti + (int64_t)q * stride);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    double v[M];
+    {
+      const double *mine = tile + (size_t)r0 * W + w;
+#pragma unroll
+      for (int q = 0; q < M; ++q) v[q] = (q < rows) ? mine[q * W] : 0.0;
+    }
+    __syncthreads();                       // tile buffer is free again
+    if (leader && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+    double yf, last;
+    if (full) {
+      yf = chunk_forward_full<M>(v, tb, pitch);
+      last = v[M - 1];
+    } else {
+      yf = chunk_forward_short<M>(v, tb, pitch, rows, &last);
+    }
+    Y[(2 * p) * W + w] = yf;
+    Y[(2 * p + 1) * W + w] = last;
+    __syncthreads();
+    const double E = chunk_interface(ge, Y, P, W, w);
+    Es[p * W + w] = E;
+    __syncthreads();
+    const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
+    if (full)
+      chunk_backward_full<M>(v, tb, pitch, alpha, E);
+    else
+      chunk_backward_short<M>(v, tb, pitch, rows, alpha, E);
+    if (live) {
+      if (FINAL) {
+        const double *ti = Tin + off;
+        double *to = Tout + off;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          if (q < rows) *to = *ti + v[q];
+          ti += stride;
+          to += stride;
+        }
+      } else {
+        double *dst = data + off;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          if (q < rows) *dst = v[q];
+          dst += stride;
+        }
+      }
+    }
+    // Y/Es are rewritten only after the next tile's first __syncthreads
+  }
+}
+
+template <int M, bool FINAL>
+int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double *Tin, double *Tout, int L,
+               int64_t stride, int n_groups, int lines_per_group, int64_t group_stride, cudaStream_t st, bool *done) {
+  *done = false;
+  const int P = ax.n_chunks;
+  constexpr int W = 16;
+  if (P * W > 256) return HS2_OK;
+  static const bool disabled = getenv("HS2_NO_TMA") != nullptr && getenv("HS2_NO_TMA")[0] == '1';
+  if (disabled) return HS2_OK;
+  // z-lines put consecutive rows 8*ny*nx bytes apart (a different 2 MB page per
+  // row); measured on B200 the tensor copy engine then delivers < half the
+  // bandwidth of plain loads (profiles/NOTES_r01.md), so the z-sweep keeps the
+  // register-load kernel unless HS2_TMA_Z=1.
+  static const bool enabled_z = getenv("HS2_TMA_Z") != nullptr && getenv("HS2_TMA_Z")[0] == '1';
+  if (group_stride == 0 && !enabled_z) return HS2_OK;
+  static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 1;
+  const int BR = L < 256 ? L : 256;
+  const int n_boxes = (L + BR - 1) / BR;
+  const size_t smem = ((size_t)n_boxes * BR * W + 3 * (size_t)P * W) * sizeof(double) + 16;
+  if (smem > 110 * 1024) return HS2_OK;
+  CUtensorMap tmap;
+  bool ok;
+  if (group_stride)
+    ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, (uint64_t)n_groups, W, BR, 1);
+  else
+    ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
+  if (!ok) return HS2_OK;
+  const int tiles_per_group = (lines_per_group + W - 1) / W;
+  const int64_t n_tiles = (int64_t)n_groups * tiles_per_group;
+  if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
+  auto kern = strided_sweep_tma<M, W, FINAL>;
+  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = pl->sm_count * 2;
+  if (grid > n_tiles) grid = (int)n_tiles;
+  dim3 block(W, P);
+  kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, stride,
+                                  tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  *done = true;
+  return HS2_OK;
+}
+
 template <int M, bool FINAL>
 int launch(const hs2_axis_tables &ax, double *data, const double *Tin, double *Tout, int L, int64_t stride,
            int n_groups, int lines_per_group, int64_t group_stride, cudaStream_t st) {
@@ -137,8 +294,16 @@ int launch(const hs2_axis_tables &ax, double *data, const double *Tin, double *T
 }
 
 template <bool FINAL>
-int dispatch(const hs2_axis_tables &ax, double *data, const double *Tin, double *Tout, int L, int64_t stride,
-             int n_groups, int lines_per_group, int64_t group_stride, cudaStream_t st) {
+int dispatch(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double *Tin, double *Tout, int L,
+             int64_t stride, int n_groups, int lines_per_group, int64_t group_stride, cudaStream_t st) {
+  bool done = false;
+  int rc = HS2_OK;
+  switch (ax.chunk) {
+    case 8: rc = launch_tma<8, FINAL>(pl, ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st, &done); break;
+    case 16: rc = launch_tma<16, FINAL>(pl, ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st, &done); break;
+    case 32: rc = launch_tma<32, FINAL>(pl, ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st, &done); break;
+  }
+  if (rc || done) return rc;
   switch (ax.chunk) {
     case 8: return launch<8, FINAL>(ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st);
     case 16: return launch<16, FINAL>(ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st);
@@ -162,11 +327,11 @@ bool hs2_tile_supported(const hs2_plan *p, int axis) {
 int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st) {
   const hs2_plan_desc &d = p->d;
   HS2_REQUIRE(d.nx < ((int64_t)1 << 31) && d.nz < ((int64_t)1 << 31), "grid too large");
-  return dispatch<false>(d.axis[1], W, nullptr, nullptr, (int)d.ny, d.nx, (int)d.nz, (int)d.nx, d.ny * d.nx, st);
+  return dispatch<false>(p, d.axis[1], W, nullptr, nullptr, (int)d.ny, d.nx, (int)d.nz, (int)d.nx, d.ny * d.nx, st);
 }
 
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st) {
   const hs2_plan_desc &d = p->d;
   HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
-  return dispatch<true>(d.axis[2], W, T, Tout, (int)d.nz, d.ny * d.nx, 1, (int)(d.ny * d.nx), 0, st);
+  return dispatch<true>(p, d.axis[2], W, T, Tout, (int)d.nz, d.ny * d.nx, 1, (int)(d.ny * d.nx), 0, st);
 }

@@ -9,11 +9,12 @@ import sys
 
 rep = sys.argv[1]
 minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+only = sys.argv[3] if len(sys.argv) > 3 else None      # substring of the kernel name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 agg = collections.OrderedDict()
-cur_file, last_line = None, None
+cur_file, last_line, cur_fn = None, None, ""
 hdr = None
 for r in rows:
     if not r:
@@ -22,6 +23,7 @@ for r in rows:
         cur_file = r[1].split("/")[-1]
         continue
     if r[0] == "Function Name":
+        cur_fn = r[1]
         continue
     if r[0] == "Line No":
         hdr = r
@@ -30,6 +32,8 @@ for r in rows:
         continue
     if r[0] != "":
         last_line = (cur_file, int(r[0]), r[1].strip()[:72])
+    if only is not None and only not in cur_fn:
+        continue
     if len(r) > 2 and r[2].startswith("0x") and last_line is not None:
         i_s = hdr.index("Warp Stall Sampling (All Samples)")
         i_e = hdr.index("Instructions Executed")
