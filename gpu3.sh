@@ -1,5 +1,5 @@
-for V in "HS2_PREFETCH=0" "HS2_PREFETCH=1" "HS2_NO_TMA_Z=1"; do
-echo $V
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for V in "HS2_X=1"; do
 env $V timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())

@@ -74,52 +74,89 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   const double *Tk = T + kbase;
   const CID *cidk = cid + kbase;
   const bool has_src = dense != nullptr || st.n > 0;
-  for (int i = tid; i < nx; i += nthreads) {
+  constexpr int RH = R / 2;               // rows handled per register batch
+  // each thread owns two adjacent columns (i, i+1): 16-byte global accesses,
+  // and the x neighbours inside the pair come from registers
+  for (int i = 2 * tid; i < nx; i += 2 * nthreads) {
     const int im = i > 0 ? i - 1 : 0;
-    const int ip = i < nx - 1 ? i + 1 : nx - 1;
-    double tcol[R + 2], xm[R], xp[R], zm[R], zp[R];
-    int id[R];
-    // issue every load of the column strip before any arithmetic
+    const int ip = i + 2 < nx ? i + 2 : nx - 1;
+    double *bcol0 = buf + i + i / M;
+    double *bcol1 = buf + (i + 1) + (i + 1) / M;
+    int last_id = -1;
+    double2 cx = make_double2(0, 0), cy = cx, cz = cx;
+    double csrc = 0.0;
 #pragma unroll
-    for (int r = -1; r <= R; ++r) {
-      int j = j0 + r;
-      j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
-      tcol[r + 1] = Tk[(int64_t)j * nx + i];
-    }
+    for (int h = 0; h < 2; ++h) {
+      const int rb = h * RH;
+      double2 tcol[RH + 2], zm[RH], zp[RH];
+      double xm[RH], xp[RH];
+      int id[RH];
+      // issue every load of the batch before any arithmetic
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int j = min(j0 + r, ny - 1);
-      const int64_t rowo = (int64_t)j * nx;
-      xm[r] = Tk[rowo + im];
-      xp[r] = Tk[rowo + ip];
-      zm[r] = zlo[rowo + i];
-      zp[r] = zhi[rowo + i];
-      id[r] = (int)cidk[rowo + i];
-    }
-    double *bcol = buf + i + i / M;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double tc = tcol[r + 1];
-      const double2 *c2 = reinterpret_cast<const double2 *>(coef + id[r] * HS2_COEF_STRIDE);
-      const double2 cx = c2[0], cy = c2[1], cz = c2[2];
-      double rr = cx.x * (xm[r] - tc);
-      rr = fma(cx.y, xp[r] - tc, rr);
-      rr = fma(cy.x, tcol[r] - tc, rr);
-      rr = fma(cy.y, tcol[r + 2] - tc, rr);
-      rr = fma(cz.x, zm[r] - tc, rr);
-      rr = fma(cz.y, zp[r] - tc, rr);
-      if (has_src && r < nrows) {
-        const int64_t idx = kbase + (int64_t)(j0 + r) * nx + i;
-        double s = dense ? dense[idx] : 0.0;
-        if (st.n) {
-          const uint8_t vv = vol[idx];
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < st.n && st.idx[q] == vv) s += st.val[q];
-        }
-        rr = fma(c2[3].x, s, rr);
+      for (int r = -1; r <= RH; ++r) {
+        int j = j0 + rb + r;
+        j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
+        tcol[r + 1] = *reinterpret_cast<const double2 *>(Tk + (int64_t)j * nx + i);
       }
-      bcol[r * Sr] = rr;
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const int j = min(j0 + rb + r, ny - 1);
+        const int64_t rowo = (int64_t)j * nx;
+        xm[r] = Tk[rowo + im];
+        xp[r] = Tk[rowo + ip];
+        zm[r] = *reinterpret_cast<const double2 *>(zlo + rowo + i);
+        zp[r] = *reinterpret_cast<const double2 *>(zhi + rowo + i);
+        if (sizeof(CID) == 1)
+          id[r] = *reinterpret_cast<const uint16_t *>(cidk + rowo + i);
+        else
+          id[r] = (int)*reinterpret_cast<const uint32_t *>(cidk + rowo + i);
+      }
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const double2 tc = tcol[r + 1];
+        const int id0 = sizeof(CID) == 1 ? (id[r] & 0xff) : (id[r] & 0xffff);
+        const int id1 = sizeof(CID) == 1 ? ((id[r] >> 8) & 0xff) : ((id[r] >> 16) & 0xffff);
+        double out[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int idc = c ? id1 : id0;
+          if (idc != last_id) {             // interior cells share one class: usually not taken
+            const double2 *c2 = reinterpret_cast<const double2 *>(coef + idc * HS2_COEF_STRIDE);
+            cx = c2[0];
+            cy = c2[1];
+            cz = c2[2];
+            csrc = c2[3].x;
+            last_id = idc;
+          }
+          const double t0 = c ? tc.y : tc.x;
+          const double vxm = c ? tc.x : xm[r];
+          const double vxp = c ? xp[r] : tc.y;
+          const double vym = c ? tcol[r].y : tcol[r].x;
+          const double vyp = c ? tcol[r + 2].y : tcol[r + 2].x;
+          const double vzm = c ? zm[r].y : zm[r].x;
+          const double vzp = c ? zp[r].y : zp[r].x;
+          double rr = cx.x * (vxm - t0);
+          rr = fma(cx.y, vxp - t0, rr);
+          rr = fma(cy.x, vym - t0, rr);
+          rr = fma(cy.y, vyp - t0, rr);
+          rr = fma(cz.x, vzm - t0, rr);
+          rr = fma(cz.y, vzp - t0, rr);
+          if (has_src && rb + r < nrows) {
+            const int64_t idx = kbase + (int64_t)(j0 + rb + r) * nx + i + c;
+            double sv = dense ? dense[idx] : 0.0;
+            if (st.n) {
+              const uint8_t vv = vol[idx];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q < st.n && st.idx[q] == vv) sv += st.val[q];
+            }
+            rr = fma(csrc, sv, rr);
+          }
+          out[c] = rr;
+        }
+        bcol0[(rb + r) * Sr] = out[0];
+        bcol1[(rb + r) * Sr] = out[1];
+      }
     }
   }
   __syncthreads();
@@ -171,14 +208,15 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
 
   // ------------------------------------------------ phase 3: coalesced store
   double *Wk = Wout + kbase + (int64_t)j0 * nx;
-  for (int i = tid; i < nx; i += nthreads) {
-    const double *bcol = buf + i + i / M;
-    double o[R];
+  for (int i = 2 * tid; i < nx; i += 2 * nthreads) {
+    const double *bcol0 = buf + i + i / M;
+    const double *bcol1 = buf + (i + 1) + (i + 1) / M;
+    double2 o[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) o[r] = bcol[r * Sr];
+    for (int r = 0; r < R; ++r) o[r] = make_double2(bcol0[r * Sr], bcol1[r * Sr]);
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (r < nrows) Wk[(int64_t)r * nx + i] = o[r];
+      if (r < nrows) *reinterpret_cast<double2 *>(Wk + (int64_t)r * nx + i) = o[r];
   }
 }
 
@@ -240,6 +278,7 @@ bool hs2_tile_x_supported(const hs2_plan *p) {
   if (!hs2_tile_supported(p, 0)) return false;
   const hs2_plan_desc &d = p->d;
   if (d.nx >= ((int64_t)1 << 30) || d.ny >= ((int64_t)1 << 30) || d.nz >= ((int64_t)1 << 30)) return false;
+  if (d.nx & 1) return false;             // column pairs need 16-byte aligned rows
   return d.axis[0].n_chunks * R <= 256;
 }
 
