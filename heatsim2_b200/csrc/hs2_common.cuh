@@ -16,6 +16,24 @@ struct hs2_plan {
 
 void hs2_set_error(const char *fmt, ...);
 
+// Optional phase timing (build with -DHS2_PHASE_TIMING): thread 0 of every
+// block adds the cycles spent between marks to g_hs2_phase[slot].
+#ifdef HS2_PHASE_TIMING
+static __device__ unsigned long long g_hs2_phase[16];   // one copy per translation unit
+#define HS2_MARK_DECL long long hs2_t0__ = clock64()
+#define HS2_MARK(slot)                                                          \
+  do {                                                                          \
+    if (threadIdx.x == 0 && threadIdx.y == 0) {                                 \
+      const long long t__ = clock64();                                          \
+      atomicAdd(&g_hs2_phase[slot], (unsigned long long)(t__ - hs2_t0__));      \
+      hs2_t0__ = t__;                                                           \
+    }                                                                           \
+  } while (0)
+#else
+#define HS2_MARK_DECL
+#define HS2_MARK(slot)
+#endif
+
 #define HS2_CUDA_CHECK(call)                                                   \
   do {                                                                         \
     cudaError_t e__ = (call);                                                  \

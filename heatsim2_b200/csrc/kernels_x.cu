@@ -52,6 +52,7 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   double *Y = buf + R * Sr;               // [2P][R]
   double *Es = Y + 2 * P * R;             // [P][R]
   double *cfs = Es + P * R;               // [n_classes][8] when coef_in_smem
+  HS2_MARK_DECL;
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
   const int k = blockIdx.x / tiles_y;
@@ -159,7 +160,9 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
       }
     }
   }
+  HS2_MARK(0);
   __syncthreads();
+  HS2_MARK(1);
 
   // ------------------------------------------------ phase 2: solve along x
   const int r = tid % R;
@@ -190,10 +193,14 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
     Y[(2 * p) * R + r] = yf;
     Y[(2 * p + 1) * R + r] = last;
   }
+  HS2_MARK(2);
   __syncthreads();
+  HS2_MARK(3);
   const double E = chunk_interface(ge, Y, P, R, r);
   if (p < P) Es[p * R + r] = E;
+  HS2_MARK(4);
   __syncthreads();
+  HS2_MARK(5);
   const double alpha = (p > 0 && p < P) ? Es[(p - 1) * R + r] : 0.0;
   if (full)
     chunk_backward_full<M>(v, tb, pitch, alpha, E);
@@ -204,7 +211,9 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
     for (int t = 0; t < M; ++t)
       if (t < rows) mine[t] = v[t];
   }
+  HS2_MARK(6);
   __syncthreads();
+  HS2_MARK(7);
 
   // ------------------------------------------------ phase 3: coalesced store
   double *Wk = Wout + kbase + (int64_t)j0 * nx;
@@ -218,6 +227,7 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
     for (int r = 0; r < R; ++r)
       if (r < nrows) *reinterpret_cast<double2 *>(Wk + (int64_t)r * nx + i) = o[r];
   }
+  HS2_MARK(8);
 }
 
 int make_src_tab(const hs2_source *src, SrcTab *st) {
@@ -290,3 +300,14 @@ int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *
   if (p->d.class_id_bytes == 1) return dispatch_x<uint8_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
   return dispatch_x<uint16_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
 }
+
+#ifdef HS2_PHASE_TIMING
+extern "C" int hs2_debug_phase(unsigned long long *out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_hs2_phase, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_hs2_phase, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
