@@ -1,5 +1,6 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for V in "HS2_X=1"; do
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+for V in "HS2_CHUNK=32" "HS2_CHUNK=16"; do
+echo $V
 env $V timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())

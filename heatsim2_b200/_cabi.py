@@ -22,7 +22,7 @@ class AxisTables(ctypes.Structure):
         ("d_line_id", c_void_p), ("d_lu", c_void_p),
         ("d_tab", c_void_p), ("d_GE", c_void_p),
         ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
-        ("pitch", ctypes.c_int32),
+        ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 

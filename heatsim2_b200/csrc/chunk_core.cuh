@@ -105,12 +105,17 @@ __device__ __forceinline__ void chunk_backward_short(double (&v)[M], const doubl
 }
 
 // E_p = row p of the inverse interface operator applied to the interleaved
-// (yf_0, yl_0, yf_1, yl_1, ...) values of this line held in Y[2P][ld] column w
-__device__ __forceinline__ double chunk_interface(const double *__restrict__ ge, const double *Y, int P, int ld, int w) {
+// (yf_0, yl_0, yf_1, yl_1, ...) values of this line held in Y[2P][ld] column w.
+// The operator decays geometrically away from the diagonal; `band` (from the
+// host, chunk_factors) is the half-width beyond which every entry is below
+// 1e-18 of the row maximum, so only chunks p-band..p+band are visited.
+__device__ __forceinline__ double chunk_interface(const double *__restrict__ ge, const double *Y, int P, int ld, int w,
+                                                  int p, int band) {
   double e0 = 0.0, e1 = 0.0;
   const double2 *g2 = reinterpret_cast<const double2 *>(ge);
+  const int q0 = max(0, p - band), q1 = min(P - 1, p + band);
 #pragma unroll 4
-  for (int q = 0; q < P; ++q) {
+  for (int q = q0; q <= q1; ++q) {
     const double2 g = __ldg(g2 + q);
     e0 = fma(g.x, Y[(2 * q) * ld + w], e0);
     e1 = fma(g.y, Y[(2 * q + 1) * ld + w], e1);

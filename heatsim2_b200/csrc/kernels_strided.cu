@@ -29,7 +29,7 @@ template <int M, int W, bool FINAL>
 __global__ void __launch_bounds__(M >= 32 ? 256 : 512, 2)
 strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
               const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
-              int L, int pitch, int P,
+              int L, int pitch, int P, int band,
               int64_t stride,          // elements between consecutive rows of a line
               int tiles_per_group,     // tiles per contiguous group of lines
               int lines_per_group,     // lines in a group (y: nx, z: ny*nx)
@@ -72,7 +72,7 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
   Y[(2 * p) * W + w] = yf;
   Y[(2 * p + 1) * W + w] = last;
   __syncthreads();
-  const double E = chunk_interface(ge, Y, P, W, w);
+  const double E = chunk_interface(ge, Y, P, W, w, p, band);
   Es[p * W + w] = E;
   __syncthreads();
   const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
@@ -126,7 +126,7 @@ template <int M, int W, bool FINAL>
 __global__ void __launch_bounds__(256, 2)
 strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__ data, const double *__restrict__ Tin,
                   double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
-                  const double *__restrict__ GE, int L, int pitch, int P, int64_t stride, int tiles_per_group,
+                  const double *__restrict__ GE, int L, int pitch, int P, int band, int64_t stride, int tiles_per_group,
                   int lines_per_group, int64_t group_stride, int n_tiles, int BR, int n_boxes, int do_prefetch) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double *tile = reinterpret_cast<double *>(smraw);              // [n_boxes*BR][W]
@@ -196,7 +196,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     Y[(2 * p) * W + w] = yf;
     Y[(2 * p + 1) * W + w] = last;
     __syncthreads();
-    const double E = chunk_interface(ge, Y, P, W, w);
+    const double E = chunk_interface(ge, Y, P, W, w, p, band);
     Es[p * W + w] = E;
     __syncthreads();
     const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
@@ -262,7 +262,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   int grid = pl->sm_count * 2;
   if (grid > n_tiles) grid = (int)n_tiles;
   dim3 block(W, P);
-  kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, stride,
+  kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band, stride,
                                   tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
   HS2_CUDA_CHECK(cudaGetLastError());
   *done = true;
@@ -283,11 +283,11 @@ int launch(const hs2_axis_tables &ax, double *data, const double *Tin, double *T
   const size_t smem = (size_t)3 * P * W * sizeof(double);
   if (W == 16)
     strided_sweep<M, 16, FINAL><<<(unsigned)blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L,
-                                                                      ax.pitch, P, stride, tiles_per_group,
+                                                                      ax.pitch, P, ax.band, stride, tiles_per_group,
                                                                       lines_per_group, group_stride);
   else
     strided_sweep<M, 8, FINAL><<<(unsigned)blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L,
-                                                                     ax.pitch, P, stride, tiles_per_group,
+                                                                     ax.pitch, P, ax.band, stride, tiles_per_group,
                                                                      lines_per_group, group_stride);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;

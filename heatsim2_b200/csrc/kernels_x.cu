@@ -39,13 +39,13 @@ __host__ __device__ inline int row_pitch(int P, int M) {
 }
 
 template <int M, typename CID>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (M >= 32 ? 2 : 4))
 sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CID *__restrict__ cid,
                const double *__restrict__ coef_g, int n_classes, int coef_in_smem,
                const uint8_t *__restrict__ vol, SrcTab st, const double *__restrict__ dense,
                const double *__restrict__ halo_lo, const double *__restrict__ halo_hi,
                const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
-               int nz, int ny, int nx, int pitch, int P, int tiles_y) {
+               int nz, int ny, int nx, int pitch, int P, int band, int tiles_y) {
   extern __shared__ double sm[];
   const int Sr = row_pitch(P, M);
   double *buf = sm;                       // [R][Sr]
@@ -196,7 +196,7 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   HS2_MARK(2);
   __syncthreads();
   HS2_MARK(3);
-  const double E = chunk_interface(ge, Y, P, R, r);
+  const double E = chunk_interface(ge, Y, P, R, r, pc, band);
   if (p < P) Es[p * R + r] = E;
   HS2_MARK(4);
   __syncthreads();
@@ -265,7 +265,7 @@ int launch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, con
   const double *dense = src ? src->d_dense : nullptr;
   kern<<<(unsigned)blocks, threads, smem, st>>>(T, W, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes, coef_in_smem,
                                                  vol, tabsrc, dense, halo_lo, halo_hi, ax.d_line_id, ax.d_tab, ax.d_GE,
-                                                 (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, tiles_y);
+                                                 (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, ax.band, tiles_y);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }

@@ -139,6 +139,18 @@ def chunk_factors(lo, dg, hi, M):
     return tab, GE
 
 
+def interface_band(GE, tol=1e-16):
+    """Half-width, in chunks, outside which every entry of every GE row is
+    below ``tol`` times the row maximum (the interface operator decays
+    geometrically away from the diagonal)."""
+    nu, P, _ = GE.shape
+    mag = np.maximum(np.abs(GE[:, :, 0::2]), np.abs(GE[:, :, 1::2]))        # [nu, P(row), P(col)]
+    rowmax = mag.max(axis=2, keepdims=True)
+    dist = np.abs(np.arange(P)[:, None] - np.arange(P)[None, :])
+    sig = mag > tol * rowmax
+    return int((dist[None, :, :] * sig).max()) if sig.any() else 0
+
+
 class AdiPlan(object):
     def __init__(self, shape, class_id, class_coef, dt, volume_array, volumetric_elements=None,
                  materials=None):
@@ -254,6 +266,7 @@ class AdiPlan(object):
             if self.d_chunk[a] is not None:
                 ax.d_tab, ax.d_GE = (t.data_ptr() for t in self.d_chunk[a])
                 ax.pitch = self.d_chunk[a][0].shape[2]
+                ax.band = interface_band(self.chunk_tabs[a][1])
         desc.device = dev.index
         desc.flags = self.flags
         handle = ctypes.c_void_p()

@@ -72,6 +72,8 @@ typedef struct hs2_axis_tables {
   int32_t chunk;
   int32_t n_chunks;
   int32_t pitch;             /* doubles per table plane (even, >= L)           */
+  int32_t band;              /* half-width (in chunks) of d_GE rows worth applying */
+  int32_t reserved;
 } hs2_axis_tables;
 
 /* Axis numbering used by every per-axis array: 0 = x (contiguous), 1 = y,

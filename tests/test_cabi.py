@@ -28,8 +28,8 @@ def test_struct_layout_matches_header():
     import ctypes
     from heatsim2_b200 import _cabi
     # axis tables: 5 pointers + 4 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x2
-    assert ctypes.sizeof(_cabi.AxisTables) == 32 + 16
-    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 48 + 8
+    assert ctypes.sizeof(_cabi.AxisTables) == 32 + 24
+    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 56 + 8
     assert ctypes.sizeof(_cabi.Source) == 24
 
 
