@@ -1,0 +1,3 @@
+nvidia-smi -L
+timeout 900 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -5
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tail -3

@@ -195,28 +195,26 @@ def _classify(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device):
     return class_id, keys, decode
 
 
-def setup(z0, y0, x0,
-          dz, dy, dx,
-          nz, ny, nx,
-          dt,
-          materials,
-          boundaries,
-          volumetric,
-          material_elements,
-          boundary_z_elements,
-          boundary_y_elements,
-          boundary_x_elements,
-          volumetric_elements,
-          top_surface_y_curvatures=None,
-          top_surface_x_curvatures=None,
-          unaligned_anisotropic=False,
-          device=None):
-    """Compile a heat-conduction problem into ``(ADI_params, ADI_steps)``.
-
-    Arguments as in the reference (crank_nicolson.pyx:128-142).  ``device``
-    (extension) picks the CUDA device; default is the current one.  Outer faces
-    that would conduct out of the grid raise ValueError (the reference calls
-    exit(1), alternatingdirection_c.c:160-163)."""
+def compile_problem(z0, y0, x0,
+                    dz, dy, dx,
+                    nz, ny, nx,
+                    dt,
+                    materials,
+                    boundaries,
+                    volumetric,
+                    material_elements,
+                    boundary_z_elements,
+                    boundary_y_elements,
+                    boundary_x_elements,
+                    volumetric_elements,
+                    top_surface_y_curvatures=None,
+                    top_surface_x_curvatures=None,
+                    unaligned_anisotropic=False,
+                    device=None):
+    """Discretise and classify: returns ``(class_id, coefs, volume_array, vol)``
+    with ``class_id`` an int32 tensor [nz,ny,nx] of equation-class indices and
+    ``coefs`` [n_classes, 8] = (M, gx-,gx+,gy-,gy+,gz-,gz+, D) per class.
+    Shared by :func:`setup` (one GPU) and ``dist.setup`` (z-slabs)."""
     from . import TEMPERATURE_COMPUTE, TEMPERATURE_FIXED
     nz, ny, nx = int(nz), int(ny), int(nx)
     if top_surface_y_curvatures is not None or top_surface_x_curvatures is not None:
@@ -233,7 +231,6 @@ def setup(z0, y0, x0,
 
     evalboundaries = evaluate_boundaries(boundaries, dz, dy, dx)
     volume_array = dz * dy * dx
-    (ADI_params, ADI_steps) = alternatingdirection.adi_setup((nz, ny, nx), volume_array)
 
     work_dev = torch.device("cpu")
     if torch.cuda.is_available():
@@ -282,6 +279,37 @@ def setup(z0, y0, x0,
         lut = torch.from_numpy(merged.reshape(-1).astype(np.int32)).to(class_id.device)
         class_id = lut[class_id.long()]
         coefs = ucoefs
+    return class_id, coefs, volume_array, vol
+
+
+def setup(z0, y0, x0,
+          dz, dy, dx,
+          nz, ny, nx,
+          dt,
+          materials,
+          boundaries,
+          volumetric,
+          material_elements,
+          boundary_z_elements,
+          boundary_y_elements,
+          boundary_x_elements,
+          volumetric_elements,
+          top_surface_y_curvatures=None,
+          top_surface_x_curvatures=None,
+          unaligned_anisotropic=False,
+          device=None):
+    """Compile a heat-conduction problem into ``(ADI_params, ADI_steps)``.
+
+    Arguments as in the reference (crank_nicolson.pyx:128-142).  ``device``
+    (extension) picks the CUDA device; default is the current one.  Outer faces
+    that would conduct out of the grid raise ValueError (the reference calls
+    exit(1), alternatingdirection_c.c:160-163)."""
+    nz, ny, nx = int(nz), int(ny), int(nx)
+    class_id, coefs, volume_array, vol = compile_problem(
+        z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric, material_elements,
+        boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements,
+        top_surface_y_curvatures, top_surface_x_curvatures, unaligned_anisotropic, device)
+    (ADI_params, ADI_steps) = alternatingdirection.adi_setup((nz, ny, nx), volume_array)
     ADI_params.plan = AdiPlan((nz, ny, nx), class_id, coefs, dt, volume_array, volumetric_elements=vol,
                               materials=materials)
     return (ADI_params, ADI_steps)

@@ -79,8 +79,20 @@ int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream) {
 
 int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_T_out && d_work, "hs2_sweep_z: NULL argument");
+  HS2_REQUIRE(plan->d.z_chunks_global == 0, "hs2_sweep_z: slab plans use hs2_sweep_z_forward/backward");
   if (hs2_tile_supported(plan, 2)) return hs2_tile_sweep_z(plan, d_T_in, d_T_out, d_work, (cudaStream_t)stream);
   return hs2_v1_sweep_z(plan, d_T_in, d_T_out, d_work, (cudaStream_t)stream);
+}
+
+int hs2_sweep_z_forward(hs2_plan *plan, double *d_work, double *d_Y, void *stream) {
+  HS2_REQUIRE(plan && d_work && d_Y, "hs2_sweep_z_forward: NULL argument");
+  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, (cudaStream_t)stream);
+}
+
+int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const double *d_Yall,
+                         void *stream) {
+  HS2_REQUIRE(plan && d_T_in && d_T_out && d_work && d_Yall, "hs2_sweep_z_backward: NULL argument");
+  return hs2_zdist(plan, 1, d_work, d_T_in, d_T_out, const_cast<double *>(d_Yall), (cudaStream_t)stream);
 }
 
 int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const hs2_source *src,
@@ -89,6 +101,7 @@ int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_wo
   if (rc) return rc;
   rc = hs2_sweep_y(plan, d_work, stream);
   if (rc) return rc;
+  HS2_REQUIRE(plan->d.z_chunks_global == 0, "hs2_step: slab plans are stepped with hs2_sweep_x/y + hs2_sweep_z_forward/backward");
   return hs2_sweep_z(plan, d_T_in, d_T_out, d_work, stream);
 }
 

@@ -315,8 +315,120 @@ int dispatch(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// z-sweep of a z-slab decomposition (one slab per GPU).  The global z-line is
+// cut into chunks of M rows; a slab owns P_loc consecutive chunks
+// [chunk0, chunk0 + P_loc).  Phase 1 (z_forward) eliminates every local chunk
+// and publishes its (y_first, y_last); the host layer all-gathers those 2
+// doubles per chunk per line over NCCL; phase 2 (z_backward) applies the rows
+// p-1 and p of the GLOBAL inverse interface operator to get alpha and E and
+// back-substitutes.  No transpose of the field is ever needed.
+template <int M, int W>
+__global__ void __launch_bounds__(256, 2)
+z_forward(double *__restrict__ data, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
+          double *__restrict__ Yloc, int pitch, int row0, int64_t stride, int n_lines) {
+  const int w = threadIdx.x, p = threadIdx.y;
+  const int col = blockIdx.x * W + w;
+  if (col >= n_lines) return;
+  const uint32_t lid = line_id[col];
+  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+  double *ptr = data + col + (int64_t)p * M * stride;
+  double v[M];
+#pragma unroll
+  for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
+  const double yf = chunk_forward_full<M>(v, tb, pitch);
+#pragma unroll
+  for (int t = 0; t < M; ++t) ptr[(int64_t)t * stride] = v[t];
+  Yloc[(int64_t)(2 * p) * n_lines + col] = yf;
+  Yloc[(int64_t)(2 * p + 1) * n_lines + col] = v[M - 1];
+}
+
+template <int M, int W>
+__global__ void __launch_bounds__(256, 2)
+z_backward(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
+           const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
+           const double *__restrict__ Yall, int pitch, int row0, int P_glob, int chunk0, int band, int64_t stride,
+           int n_lines) {
+  const int w = threadIdx.x, p = threadIdx.y;
+  const int col = blockIdx.x * W + w;
+  if (col >= n_lines) return;
+  const uint32_t lid = line_id[col];
+  const int pg = chunk0 + p;
+  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+  const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
+  const int64_t off = col + (int64_t)p * M * stride;
+  double v[M];
+#pragma unroll
+  for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
+  // rows pg (-> E) and pg-1 (-> alpha) of the inverse interface operator
+  double E = 0.0, alpha = 0.0;
+  {
+    const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
+    for (int q = q0; q <= q1; ++q) {
+      const double2 g = __ldg(reinterpret_cast<const double2 *>(ge) + q);
+      E = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + col], E);
+      E = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + col], E);
+    }
+    if (pg > 0) {
+      const double *gm = ge - 2 * P_glob;
+      const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
+      for (int q = a0; q <= a1; ++q) {
+        const double2 g = __ldg(reinterpret_cast<const double2 *>(gm) + q);
+        alpha = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + col], alpha);
+        alpha = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + col], alpha);
+      }
+    }
+  }
+  chunk_backward_full<M>(v, tb, pitch, alpha, E);
+#pragma unroll
+  for (int t = 0; t < M; ++t) Tout[off + (int64_t)t * stride] = Tin[off + (int64_t)t * stride] + v[t];
+}
+
+template <int M>
+int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, cudaStream_t st) {
+  const hs2_plan_desc &d = pl->d;
+  const hs2_axis_tables &ax = d.axis[2];
+  const int P_loc = (int)(d.nz / M);
+  const int W = P_loc * 16 <= 256 ? 16 : 8;
+  HS2_REQUIRE(P_loc * W <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
+  const int n_lines = (int)(d.ny * d.nx);
+  const int blocks = (n_lines + W - 1) / W;
+  const int row0 = d.z_chunk0 * M;
+  dim3 block(W, P_loc);
+  if (phase == 0) {
+    if (W == 16)
+      z_forward<M, 16><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, n_lines);
+    else
+      z_forward<M, 8><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, n_lines);
+  } else {
+    if (W == 16)
+      z_backward<M, 16><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
+                                                  d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, n_lines);
+    else
+      z_backward<M, 8><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
+                                                 d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, n_lines);
+  }
+  HS2_CUDA_CHECK(cudaGetLastError());
+  return HS2_OK;
+}
+
+int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, cudaStream_t st) {
+  const hs2_plan_desc &d = pl->d;
+  const int M = d.axis[2].chunk;
+  HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
+  HS2_REQUIRE((M == 8 || M == 16 || M == 32) && d.nz % M == 0 && d.axis[2].d_tab && d.axis[2].d_GE,
+              "distributed z sweep needs chunk tables and nz (%lld) divisible by the chunk size (%d)", (long long)d.nz, M);
+  HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
+  switch (M) {
+    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, st);
+    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, st);
+    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, st);
+  }
+}
+
 bool hs2_tile_supported(const hs2_plan *p, int axis) {
   const hs2_axis_tables &ax = p->d.axis[axis];
+  if (axis == 2 && p->d.z_chunks_global > 0) return false;   // slab plans use hs2_sweep_z_forward/backward
   if (p->d.flags & HS2_FLAG_FORCE_FALLBACK) return false;
   if (!(ax.chunk == 8 || ax.chunk == 16 || ax.chunk == 32)) return false;
   if (!ax.d_tab || !ax.d_GE || ax.pitch <= 0 || (ax.pitch & 1)) return false;

@@ -1,0 +1,175 @@
+"""Multi-GPU ADI step: z-slab decomposition over the GPUs of one node.
+
+There is no counterpart in the reference (single process, single thread).
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch); rank r
+owns planes ``[r*nz/W, (r+1)*nz/W)`` of the global ``(nz, ny, nx)`` grid, a
+contiguous block in C order.
+
+Per time step
+  1. halo exchange: the top/bottom plane of ``T`` goes to the neighbouring
+     ranks (``ny*nx*8`` bytes each way, send/recv pairs) - the explicit
+     7-point stencil of stage 0 needs ``T`` at k+-1;
+  2. x- and y-sweeps are slab-local (their lines do not cross slabs);
+  3. z-sweep: every rank eliminates its own chunks of every z-line
+     (``hs2_sweep_z_forward``), the 2 doubles per chunk per line that describe
+     the chunk to its neighbours are all-gathered (``2*nz/chunk`` doubles per
+     line in total - 0.4 % of the field for chunk = 32), and every rank
+     back-substitutes with the rows of the global inverse interface operator
+     (``hs2_sweep_z_backward``).  The field itself is never transposed or sent.
+
+The result differs from the single-GPU path only by rounding (same chunked
+algorithm; a single GPU applies the interface operator inside one kernel).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from . import alternatingdirection_c_pyx as alternatingdirection
+from . import crank_nicolson
+from .plan import AdiPlan
+
+
+def slab_range(nz, rank, world):
+    """Planes owned by ``rank``: equal slabs (nz must divide evenly)."""
+    if nz % world != 0:
+        raise ValueError("nz=%d is not divisible by the number of ranks (%d)" % (nz, world))
+    h = nz // world
+    return rank * h, (rank + 1) * h
+
+
+class DistPlan(object):
+    """Slab plan + the communication of one rank."""
+
+    def __init__(self, plan, group=None):
+        self.plan = plan
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.shape = plan.shape
+        self.global_shape = (plan.slab["nz_global"],) + plan.shape[1:]
+        self.k0 = plan.slab["k0"]
+        self.chunk = plan.chunk[2][0]
+        self.p_loc = plan.shape[0] // self.chunk
+        self._bufs = {}
+
+    # ------------------------------------------------------------- buffers
+    def _buf(self, name, shape, like):
+        b = self._bufs.get(name)
+        if b is None or tuple(b.shape) != tuple(shape) or b.device != like.device:
+            b = torch.empty(shape, dtype=torch.float64, device=like.device)
+            self._bufs[name] = b
+        return b
+
+    def _peer(self, r):
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    # ------------------------------------------------- kernels (C ABI, CUDA)
+    def _k_sweep_x(self, T_in, work, src, keep, halo_lo, halo_hi):
+        p = self.plan
+        _cabi.check(_cabi.lib().hs2_sweep_x(
+            p._handle, T_in.data_ptr(), work.data_ptr(), ctypes.byref(src) if src is not None else None,
+            halo_lo.data_ptr() if halo_lo is not None else None,
+            halo_hi.data_ptr() if halo_hi is not None else None, self._stream(T_in)))
+
+    def _k_sweep_y(self, work):
+        _cabi.check(_cabi.lib().hs2_sweep_y(self.plan._handle, work.data_ptr(), self._stream(work)))
+
+    def _k_z_forward(self, work, Y):
+        _cabi.check(_cabi.lib().hs2_sweep_z_forward(self.plan._handle, work.data_ptr(), Y.data_ptr(), self._stream(work)))
+
+    def _k_z_backward(self, T_in, T_out, work, Yall):
+        _cabi.check(_cabi.lib().hs2_sweep_z_backward(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(),
+                                                     work.data_ptr(), Yall.data_ptr(), self._stream(work)))
+
+    def _stream(self, t):
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    def _prepare(self, T_in):
+        self.plan.ensure_device(T_in.device)
+
+    # ------------------------------------------------------- communication
+    def exchange_halos(self, T_in):
+        """Send plane 0 down and plane -1 up; returns (halo_lo, halo_hi), None
+        at the domain faces."""
+        ny, nx = self.shape[1:]
+        ops = []
+        halo_lo = halo_hi = None
+        if self.rank > 0:
+            halo_lo = self._buf("halo_lo", (ny, nx), T_in)
+            ops.append(dist.P2POp(dist.isend, T_in[0], self._peer(self.rank - 1), self.group))
+            ops.append(dist.P2POp(dist.irecv, halo_lo, self._peer(self.rank - 1), self.group))
+        if self.rank < self.world - 1:
+            halo_hi = self._buf("halo_hi", (ny, nx), T_in)
+            ops.append(dist.P2POp(dist.isend, T_in[-1], self._peer(self.rank + 1), self.group))
+            ops.append(dist.P2POp(dist.irecv, halo_hi, self._peer(self.rank + 1), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return halo_lo, halo_hi
+
+    # ----------------------------------------------------------------- step
+    def step_device(self, T_in, T_out, t, dt, volumetric_elements, volumetric):
+        """One time step of this rank's slab (tensors [nz/W, ny, nx] float64 on
+        the plan's device; ``T_out`` may be ``T_in``).  Collective: every rank
+        of the group must call it."""
+        if tuple(T_in.shape) != self.shape:
+            raise ValueError("slab has shape %r, got %r" % (self.shape, tuple(T_in.shape)))
+        self._prepare(T_in)
+        ny, nx = self.shape[1:]
+        src = keep = None
+        if volumetric is not None and len(volumetric):
+            src, keep = self.plan._source(t, dt, volumetric_elements, volumetric)
+        halo_lo, halo_hi = self.exchange_halos(T_in)
+        work = self._buf("work", self.shape, T_in)
+        self._k_sweep_x(T_in, work, src, keep, halo_lo, halo_hi)
+        self._k_sweep_y(work)
+        Y = self._buf("Y", (2 * self.p_loc, ny * nx), T_in)
+        Yall = self._buf("Yall", (self.world * 2 * self.p_loc, ny * nx), T_in)
+        self._k_z_forward(work, Y)
+        dist.all_gather_into_tensor(Yall, Y, group=self.group)
+        self._k_z_backward(T_in, T_out, work, Yall)
+        if keep is not None and len(keep) > 1 and T_in.is_cuda:
+            torch.cuda.current_stream(T_in.device).synchronize()
+        return T_out
+
+    def run_step(self, t, dt, Tarray, volumetric_elements, volumetric, out=None):
+        if not isinstance(Tarray, torch.Tensor):
+            raise TypeError("distributed run_adi_steps takes this rank's slab as a torch tensor")
+        if Tarray.dtype != torch.float64:
+            raise ValueError("Tarray must be float64")
+        T_in = Tarray.contiguous()
+        T_out = torch.empty_like(T_in) if out is None else out
+        return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
+
+    # bytes this rank sends per step (for NVLink accounting in bench.py)
+    def comm_bytes_per_step(self):
+        ny, nx = self.shape[1:]
+        halo = ny * nx * 8 * ((self.rank > 0) + (self.rank < self.world - 1))
+        gather = 2 * self.p_loc * ny * nx * 8 * (self.world - 1)
+        return {"halo_send": halo, "allgather_send": gather}
+
+
+def setup(z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric,
+          material_elements, boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements,
+          group=None, device=None, plan_class=DistPlan):
+    """Distributed counterpart of ``heatsim2_b200.setup``: same GLOBAL problem
+    description on every rank; returns ``(ADI_params, ADI_steps)`` whose plan
+    steps this rank's z-slab.  ``ADI_params.slab = (k0, k1)``.
+
+    ``run_adi_steps(ADI_params, ADI_steps, t, dt, T_slab, vol_elements_slab,
+    volumetric)`` then takes and returns the local slab."""
+    nz, ny, nx = int(nz), int(ny), int(nx)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    k0, k1 = slab_range(nz, rank, world)
+    class_id, coefs, volume_array, vol = crank_nicolson.compile_problem(
+        z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric, material_elements,
+        boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements, device=device)
+    plan = AdiPlan((k1 - k0, ny, nx), None, coefs, dt, volume_array, volumetric_elements=vol[k0:k1],
+                   materials=materials, slab=(k0, class_id))
+    (ADI_params, ADI_steps) = alternatingdirection.adi_setup((nz, ny, nx), volume_array)
+    ADI_params.plan = plan_class(plan, group)
+    ADI_params.slab = (k0, k1)
+    return (ADI_params, ADI_steps)

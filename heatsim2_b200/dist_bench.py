@@ -1,0 +1,115 @@
+"""bench.py's N>1 arm: weak-scaling z-slab run, one rank per GPU (launched by
+torch.distributed.run).  Device-side timing, max over ranks, rank 0 prints."""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+METRIC = "ADI cell-updates/s (float64)"
+UNIT = "cell-updates/s"
+
+
+def run(args, shape, workload_name):
+    import heatsim2_b200 as hs
+    from heatsim2_b200 import _cabi, dist as hdist
+    import problems
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    _cabi.lib()
+    t0 = time.perf_counter()
+    prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
+    P, S = hdist.setup(*prob["setup_args"])
+    dplan = P.plan
+    dplan.plan.ensure_device(dev)
+    setup_s = time.perf_counter() - t0
+    k0, k1 = P.slab
+    n_local = (k1 - k0) * shape[1] * shape[2]
+    n_global = shape[0] * shape[1] * shape[2]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Ta = torch.rand((k1 - k0,) + tuple(shape[1:]), dtype=torch.float64, device=dev, generator=g)
+    Tb = torch.empty_like(Ta)
+    ve = prob["volumetric_elements"][k0:k1]
+    vol = prob["volumetric"]
+    dt = prob["dt"]
+    hs.run_adi_steps(P, S, 0.0, dt, Ta, ve, vol, out=Tb)        # flash step, outside the timed region
+    Ta, Tb = Tb, Ta
+    it = 1
+    for _ in range(max(args.warmup, 3)):
+        hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+        Ta, Tb = Tb, Ta
+        it += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+        Ta, Tb = Tb, Ta
+        it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms) / args.steps
+    # e2e: every step each rank uploads its slab from pinned host memory and reads the result back
+    H_in = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
+    H_out = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
+    H_in.copy_(Ta)
+    e2e_steps = max(3, min(args.steps, 5))
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        Ta.copy_(H_in, non_blocking=True)
+        hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+        H_out.copy_(Tb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        H_in, H_out = H_out, H_in
+        it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2) / e2e_steps
+    finite = torch.isfinite(Ta).all().to(torch.int32)
+    dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        peak = 6650.0
+        pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+        peak_src = "fallback (B200_PROFILING.md)"
+        if os.path.exists(pk):
+            peak, peak_src = json.load(open(pk))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy), per GPU"
+        value = n_global / (ms_step * 1e-3)
+        bytes_cell = 72          # distributed z-sweep re-reads/re-writes the increment once: 16 + 16 + 40
+        comm = dplan.comm_bytes_per_step()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(tuple(shape)), "grid": list(shape), "cells": n_global,
+                           "cells_per_gpu": n_local, "decomposition": "z-slabs, %d planes per GPU" % (k1 - k0),
+                           "l2": "inputs larger than L2", "setup_s": setup_s, "finite": bool(int(finite))},
+                "roofline": {"bound": "hbm", "kernel": "whole step (3 sweeps + z interface exchange)",
+                             "achieved": 56 * n_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": 56 * n_local / (ms_step * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src,
+                             "note": "algorithmic 56 B/cell-update; the slab z-sweep actually moves %d B/cell" % bytes_cell},
+                "comm": {"halo_bytes_per_rank_per_step": comm["halo_send"],
+                         "allgather_bytes_sent_per_rank_per_step": comm["allgather_send"],
+                         "backend": "NCCL %s over NVLink" % ".".join(str(v) for v in torch.cuda.nccl.version())},
+                "cpu_baseline": None,
+                "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_global * 8,
+                        "d2h_bytes_per_step": n_global * 8, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "api": "per rank: pinned host slab -> device, heatsim2_b200.run_adi_steps (dist plan), device -> pinned host"},
+                "gpu_launches": args.steps * 4 * world}
+        print(json.dumps(line))
+    dist.destroy_process_group()

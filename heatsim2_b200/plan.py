@@ -37,6 +37,15 @@ def _line_view(a3, axis):
     return a3.permute(1, 2, 0).reshape(ny * nx, nz)
 
 
+def slab_chunk(nz_local):
+    """Chunk size of the distributed z-solve: the largest of 32/16/8 that
+    divides the slab thickness with at most 32 chunks per slab."""
+    for M in (32, 16, 8):
+        if nz_local % M == 0 and nz_local // M <= 32:
+            return M
+    raise NotImplementedError("slab thickness %d must be a multiple of 8 (at most 32 chunks of 8/16/32 planes)" % nz_local)
+
+
 def thomas_factors(lo, dg, hi):
     """Thomas factorisation of a batch of tridiagonal lines [n_unique, L]:
     returns [n_unique, L, 4] = {1/pivot, lo/pivot, hi/pivot, 0}
@@ -152,8 +161,15 @@ def interface_band(GE, tol=1e-16):
 
 
 class AdiPlan(object):
+    """One problem (or one z-slab of it) compiled for the CUDA library.
+
+    ``slab = (k0, class_id_global)`` makes this the plan of planes
+    ``[k0, k0 + shape[0])`` of a larger grid split along z over several GPUs:
+    x- and y-line tables come from the local planes, z-line tables from the
+    global lines (the z-solve spans all slabs, see ``dist.py``)."""
+
     def __init__(self, shape, class_id, class_coef, dt, volume_array, volumetric_elements=None,
-                 materials=None):
+                 materials=None, slab=None):
         self.shape = tuple(int(s) for s in shape)
         nz, ny, nx = self.shape
         self.n = nz * ny * nx
@@ -164,14 +180,22 @@ class AdiPlan(object):
         self.n_classes = self.class_coef.shape[0]
         if self.n_classes > 65536:
             raise NotImplementedError("more than 65536 equation classes (%d)" % self.n_classes)
-        cid = class_id if isinstance(class_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(class_id))
-        want = torch.uint8 if self.n_classes <= 256 else torch.int16    # int16 carries u16 bit patterns
-        if cid.dtype != want:
-            cid = cid.to(torch.int64).to(want) if want == torch.uint8 else cid.to(torch.int32).to(torch.int16)
-        self.class_id = cid.reshape(self.shape).contiguous()
+        self.slab = None
+        if slab is None:
+            self.class_id = self._pack_ids(class_id).reshape(self.shape).contiguous()
+            self._check_closed(self.class_id)
+        else:
+            k0, gid = slab
+            gid = self._pack_ids(gid)
+            self._check_closed(gid)
+            if k0 < 0 or k0 + nz > gid.shape[0] or tuple(gid.shape[1:]) != (ny, nx):
+                raise ValueError("slab [%d,%d) does not fit the global grid %r" % (k0, k0 + nz, tuple(gid.shape)))
+            self.slab = dict(k0=int(k0), nz_global=int(gid.shape[0]))
+            self._global_ids = gid
+            self.class_id = gid[k0:k0 + nz].contiguous()
         self._setup_vol_elements = volumetric_elements
-        self._check_closed()
         self._build_lines()
+        self._global_ids = None
         self._dev = None
         self._handle = None
         # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
@@ -180,12 +204,18 @@ class AdiPlan(object):
         self._vol_dev = None
         self._vol_key = None
 
+    def _pack_ids(self, class_id):
+        cid = class_id if isinstance(class_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(class_id))
+        want = torch.uint8 if self.n_classes <= 256 else torch.int16    # int16 carries u16 bit patterns
+        if cid.dtype != want:
+            cid = cid.to(torch.int64).to(want) if want == torch.uint8 else cid.to(torch.int32).to(torch.int16)
+        return cid
+
     # ------------------------------------------------------------ validation
-    def _check_closed(self):
+    def _check_closed(self, cid):
         """No conductance may point out of the domain.  The reference detects
         this inside C add_equation and calls exit(1)
         (alternatingdirection_c.c:160-163); here it is a ValueError."""
-        cid = self.class_id
         faces = ((cid[0], GZM, "z-min"), (cid[-1], GZP, "z-max"),
                  (cid[:, 0], GYM, "y-min"), (cid[:, -1], GYP, "y-max"),
                  (cid[:, :, 0], GXM, "x-min"), (cid[:, :, -1], GXP, "x-max"))
@@ -198,27 +228,35 @@ class AdiPlan(object):
     # ------------------------------------------------------- unique line tables
     def _build_lines(self):
         cc = self.class_coef
-        M = cc[:, M_]
+        cap = cc[:, M_]
         self.scaled_coef = np.zeros((self.n_classes, _cabi.HS2_COEF_STRIDE))
-        self.scaled_coef[:, 0:6] = cc[:, GXM:GZP + 1] / M[:, None]
-        self.scaled_coef[:, 6] = cc[:, D_] / M
-        self.scaled_coef[:, 7] = M
-        cid = self.class_id
-        cid_i = (cid.to(torch.int32) & 0xFFFF) if cid.dtype == torch.int16 else cid
+        self.scaled_coef[:, 0:6] = cc[:, GXM:GZP + 1] / cap[:, None]
+        self.scaled_coef[:, 6] = cc[:, D_] / cap
+        self.scaled_coef[:, 7] = cap
+
+        def as_int(cid):
+            return (cid.to(torch.int32) & 0xFFFF) if cid.dtype == torch.int16 else cid
+
         self.line_id, self.line_lu, self.line_rows = [], [], []
         self.chunk, self.chunk_tabs = [], []
         for axis in range(3):
             gm, gp = _AXIS_G[axis]
-            rows = np.stack([-0.5 * cc[:, gm] / M, 1.0 + 0.5 * (cc[:, gm] + cc[:, gp]) / M, -0.5 * cc[:, gp] / M], axis=1)
+            rows = np.stack([-0.5 * cc[:, gm] / cap, 1.0 + 0.5 * (cc[:, gm] + cc[:, gp]) / cap, -0.5 * cc[:, gp] / cap], axis=1)
             urows, sub_of_class = np.unique(rows, axis=0, return_inverse=True)
             sub_of_class = sub_of_class.reshape(-1)
+            cid = self._global_ids if (axis == 2 and self.slab is not None) else self.class_id
             sub_lut = torch.from_numpy(sub_of_class.astype(np.int64)).to(cid.device)
-            lid, reps = _unique_lines(cid_i, sub_lut, axis, len(urows))
+            lid, reps = _unique_lines(as_int(cid), sub_lut, axis, len(urows))
             lo, dg, hi = (urows[:, c][reps] for c in range(3))
             self.line_id.append(lid)                       # int32 tensor [n_lines]
             self.line_rows.append((lo, dg, hi))            # numpy [n_unique, L] each
-            self.line_lu.append(thomas_factors(lo, dg, hi))
-            rows_per_chunk, n_chunks = choose_chunk(dg.shape[1])
+            if axis == 2 and self.slab is not None:
+                rows_per_chunk = slab_chunk(self.shape[0])
+                n_chunks = dg.shape[1] // rows_per_chunk
+                self.line_lu.append(np.zeros((dg.shape[0], 1, _cabi.HS2_LU_STRIDE)))    # whole-line path unused
+            else:
+                rows_per_chunk, n_chunks = choose_chunk(dg.shape[1])
+                self.line_lu.append(thomas_factors(lo, dg, hi))
             self.chunk.append((rows_per_chunk, n_chunks))
             self.chunk_tabs.append(chunk_factors(lo, dg, hi, rows_per_chunk) if rows_per_chunk else None)
 
@@ -269,6 +307,9 @@ class AdiPlan(object):
                 ax.band = interface_band(self.chunk_tabs[a][1])
         desc.device = dev.index
         desc.flags = self.flags
+        if self.slab is not None:
+            desc.z_chunk0 = self.slab["k0"] // self.chunk[2][0]
+            desc.z_chunks_global = self.chunk[2][1]
         handle = ctypes.c_void_p()
         with torch.cuda.device(dev):
             _cabi.check(lib.hs2_plan_create(ctypes.byref(desc), ctypes.byref(handle)))

@@ -88,6 +88,14 @@ typedef struct hs2_plan_desc {
   hs2_axis_tables axis[3];
   int32_t device;              /* CUDA device ordinal the buffers live on     */
   int32_t flags;               /* HS2_FLAG_*                                  */
+  /* z-slab decomposition (one slab per GPU).  When z_chunks_global > 0 the
+   * plan's nz planes are chunks [z_chunk0, z_chunk0 + nz/chunk) of global
+   * z-lines made of z_chunks_global chunks; axis[2] then describes the GLOBAL
+   * line: d_tab planes are indexed by global row (pitch >= global nz), d_GE is
+   * [n_unique][z_chunks_global][2*z_chunks_global], and nz must be a multiple
+   * of axis[2].chunk.  0 / 0 for a single-GPU plan.                           */
+  int32_t z_chunk0;
+  int32_t z_chunks_global;
 } hs2_plan_desc;
 
 #define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
@@ -138,6 +146,18 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work,
 int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream);
 int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out,
                 double *d_work, void *stream);
+
+/* z-sweep of a slab plan, in two halves around one collective (there is no
+ * reference counterpart: heatsim2 is single-process).
+ *   forward : eliminate the local chunks of d_work in place and write their
+ *             (y_first, y_last) pairs to d_Y [2*nz/chunk][ny*nx]
+ *   <caller all-gathers d_Y of all slabs, in slab order, into d_Yall
+ *    [2*z_chunks_global][ny*nx] - NCCL all-gather over NVLink>
+ *   backward: interface values from d_Yall, back-substitution,
+ *             d_T_out = d_T_in + increment                                    */
+int hs2_sweep_z_forward(hs2_plan *plan, double *d_work, double *d_Y, void *stream);
+int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out,
+                         double *d_work, const double *d_Yall, void *stream);
 
 /* Drop-ins for heatsim2/tridiag.pyx on device arrays.
  * hs2_tridiag_lu    = tridiaglu   (:9-43):  A[n][3] -> L[n][3], U[n][3]

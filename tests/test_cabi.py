@@ -17,7 +17,7 @@ def test_library_exports_header_symbols():
     build.build()
     L = _cabi.lib()
     names = _declared()
-    assert len(names) >= 12
+    assert len(names) >= 14
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_cabi.PROTOTYPES) == names
@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     from heatsim2_b200 import _cabi
     # axis tables: 5 pointers + 4 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x2
     assert ctypes.sizeof(_cabi.AxisTables) == 32 + 24
-    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 56 + 8
+    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 56 + 16
     assert ctypes.sizeof(_cabi.Source) == 24
 
 

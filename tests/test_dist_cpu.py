@@ -1,0 +1,100 @@
+"""Multi-GPU host logic on CPU ranks (gloo, world_size 2 and 4): slab
+partition, halo exchange, all-gather layout and the global z-line tables, with
+the kernels replaced by their numpy transcriptions (tests/emul.py).  The slab
+results must equal the oracle / the single-domain run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import adi_oracle
+import emul
+import problems
+import util
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, kwargs, nsteps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import heatsim2_b200 as hs
+        from heatsim2_b200 import dist as hdist
+        prob = problems.ALL[name](hs, **kwargs)
+        P, S = hdist.setup(*prob["setup_args"], plan_class=emul.EmulDistPlan)
+        k0, k1 = P.slab
+        T = torch.from_numpy(np.array(prob["T0"][k0:k1]))
+        ve = prob["volumetric_elements"][k0:k1]
+        for it in range(nsteps):
+            T = hs.run_adi_steps(P, S, prob["t0"] + it * prob["dt"], prob["dt"], T, ve, prob["volumetric"])
+        q.put((rank, k0, k1, T.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, name, kwargs, nsteps):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    parts.sort()
+    return np.concatenate([p[3] for p in parts], axis=0)
+
+
+@pytest.mark.parametrize("world,name,kwargs", [
+    (2, "steelonfoam", dict(nz=32, ny=12, nx=14)),
+    (4, "steelonfoam", dict(nz=64, ny=10, nx=12)),
+    (2, "composite", dict(nz=32, ny=12, nx=16, ply=4)),
+    (2, "steelonwater", dict(nz=48, ny=20, nx=24)),
+])
+def test_slabs_match_oracle(world, name, kwargs):
+    import heatsim2_b200 as hs
+    nsteps = 4
+    got = _run(world, name, kwargs, nsteps)
+    prob = problems.ALL[name](hs, **kwargs)
+    want = adi_oracle.run(prob, nsteps=nsteps)
+    assert util.relerr(got, want) <= 1e-12
+
+
+def test_emulation_matches_oracle_single_domain():
+    """the transcription itself (and hence the tables) is right"""
+    import heatsim2_b200 as hs
+    prob = problems.steelonfoam(hs, nz=24, ny=12, nx=14)
+    P, S = hs.setup(*prob["setup_args"])
+    O = adi_oracle.setup(*prob["setup_args"])
+    T = np.array(prob["T0"])
+    for it in range(3):
+        src = O.volumetric_array(it * prob["dt"], prob["dt"])
+        want = O.step(it * prob["dt"], prob["dt"], T)
+        got = emul.step_single(P.plan, T, src)
+        assert util.relerr(got, want) <= 1e-12
+        T = want
+
+
+def test_slab_partition_rules():
+    from heatsim2_b200 import dist as hdist
+    from heatsim2_b200.plan import slab_chunk
+    assert hdist.slab_range(1024, 3, 8) == (384, 512)
+    with pytest.raises(ValueError):
+        hdist.slab_range(100, 0, 8)
+    assert slab_chunk(128) == 32 and slab_chunk(16) == 16 and slab_chunk(24) == 8
+    with pytest.raises(NotImplementedError):
+        slab_chunk(20)

@@ -1,0 +1,81 @@
+"""z-slab multi-GPU path on real GPUs (NCCL): N ranks must reproduce the
+single-GPU field (<= 1e-13 relative) and the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import problems
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, kwargs, nsteps, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import heatsim2_b200 as hs
+        from heatsim2_b200 import dist as hdist
+        prob = problems.ALL[name](hs, **kwargs)
+        P, S = hdist.setup(*prob["setup_args"])
+        k0, k1 = P.slab
+        T = torch.from_numpy(np.array(prob["T0"][k0:k1])).cuda()
+        ve = prob["volumetric_elements"][k0:k1]
+        for it in range(nsteps):
+            T = hs.run_adi_steps(P, S, prob["t0"] + it * prob["dt"], prob["dt"], T, ve, prob["volumetric"])
+        torch.cuda.synchronize()
+        q.put((rank, T.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, name, kwargs, nsteps):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    parts.sort(key=lambda t: t[0])
+    return np.concatenate([p[1] for p in parts], axis=0)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name,kwargs,nsteps", [
+    ("steelonfoam", dict(nz=64, ny=40, nx=48), 6),
+    ("uniform_slab", dict(shape=(128, 48, 64)), 4),
+    ("composite", dict(nz=64, ny=32, nx=32, ply=8), 4),
+])
+def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps):
+    import adi_oracle
+    import heatsim2_b200 as hs
+    world = min(_ngpu(), 4) if name == "uniform_slab" else 2
+    got = _run(world, name, kwargs, nsteps)
+    prob = problems.ALL[name](hs, **kwargs)
+    one = util.run_b200(hs, prob, nsteps=nsteps)
+    assert util.relerr(got, one) <= 1e-13
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=nsteps)) <= 1e-12
