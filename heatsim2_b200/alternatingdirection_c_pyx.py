@@ -51,8 +51,13 @@ class pyadi_step(object):
         self.invpermuteorder = tuple(int(a) for a in np.argsort(permuteorder))
 
     def finalize(self):
-        """The reference converts COO->CSR and LU-factors here (:212-282);
-        the plan is complete as soon as setup() returns, so nothing to do."""
+        """The reference converts COO->CSR and LU-factors here (:212-282).
+        Plans made by setup() are complete already; when equations were added
+        cell by cell (add_equation_to_adi_matrices) the first finalize() turns
+        them into the class tables."""
+        builder = getattr(self.ADI_params, "_cell_builder", None)
+        if builder is not None and self.ADI_params.plan is None:
+            self.ADI_params.plan = builder.finish(None, self.ADI_params.volume_array)
         return None
 
     # --- host-side materialisation of the reference's matrices (inspection /

@@ -283,3 +283,44 @@ def test_choose_chunk_limits():
     assert choose_chunk(512) in ((16, 32), (32, 16))
     assert choose_chunk(1024) == (32, 32)
     assert choose_chunk(1025) == (0, 0)
+
+
+def test_cellwise_assembly_like_the_reference_loop():
+    """add_equation_to_adi_matrices + finalize (the reference's per-cell flow,
+    crank_nicolson.pyx:272-496) builds the same plan as the vectorised setup."""
+    from heatsim2_b200 import crank_nicolson as cn
+    prob = problems.steelonfoam(hs, nz=6, ny=5, nx=7)
+    (z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric, me, bz, by, bx, ve) = prob["setup_args"]
+    ev = cn.evaluate_boundaries(boundaries, dz, dy, dx)
+    P, S = adi.adi_setup((nz, ny, nx), dz * dy * dx)
+    T555p, T555m = ex.linear_expression("T555p"), ex.linear_expression("T555m")
+    src = ex.linear_expression("volumetric_source")
+    cache, ecache = {}, {}
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                (_, kk, rho, c) = materials[me[k, j, i]]
+                b = (bz[k, j, i], bz[k + 1, j, i], by[k, j, i], by[k, j + 1, i], bx[k, j, i], bx[k, j, i + 1])
+
+                def kn(kk2, jj2, ii2):
+                    if 0 <= kk2 < nz and 0 <= jj2 < ny and 0 <= ii2 < nx and materials[me[kk2, jj2, ii2]][0] == 0:
+                        return materials[me[kk2, jj2, ii2]][1]
+                    return kk
+                kp = (kk, kn(k, j, i + 1), kn(k, j + 1, i), kn(k + 1, j, i), kn(k, j, i - 1), kn(k, j - 1, i), kn(k - 1, j, i))
+                key = (0, b, kp, rho, c)
+                if key not in ecache:
+                    hf = ((cn.shift_expression(ev[b[0]][0], (-.5, 0, 0)) - cn.shift_expression(ev[b[1]][0], (.5, 0, 0))) * (1.0 / dz) +
+                          (cn.shift_expression(ev[b[2]][1], (0, -.5, 0)) - cn.shift_expression(ev[b[3]][1], (0, .5, 0))) * (1.0 / dy) +
+                          (cn.shift_expression(ev[b[4]][2], (0, 0, -.5)) - cn.shift_expression(ev[b[5]][2], (0, 0, .5))) * (1.0 / dx) + src)
+                    hf = cn.subst_thermal_conductivity(hf, kp)
+                    te = -(T555p - T555m) * rho * c * (1.0 / dt)
+                    ecache[key] = adi.adi_expressions(hf, te)
+                sp, tm = ecache[key]
+                adi.add_equation_to_adi_matrices(P, S, k, j, i, key, cache, sp, tm)
+    for st in S:
+        st.finalize()
+    Pv, Sv = hs.setup(*prob["setup_args"])
+    a = P.plan.class_coef[P.plan.class_id.cpu().numpy().astype(int)]
+    b = Pv.plan.class_coef[Pv.plan.class_id.cpu().numpy().astype(int)]
+    assert np.array_equal(a, b)
+    assert P.plan.n_unique == Pv.plan.n_unique
