@@ -1,7 +1,7 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for V in "HS2_CHUNK=32" "HS2_CHUNK=16"; do
+for V in "HS2_CARVEOUT=-1" "HS2_CARVEOUT=100"; do
 echo $V
-env $V timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+env $V HS2_Z_PREFETCH=0 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print('ms/step',d['ms_per_step'],'value',d['value']/1e9,'G; step frac',d['roofline']['step']['frac'], 'launches', d['gpu_launches'])

@@ -1,2 +1,3 @@
 python heatsim2_b200/build.py --force -DHS2_PHASE_TIMING 2>&1 | grep -E "error"
-python profiles/phase_timing.py 512
+HS2_Z_PREFETCH=1 python profiles/phase_timing_strided.py
+HS2_Z_PREFETCH=2 python profiles/phase_timing_strided.py | tail -9

@@ -1,7 +1,8 @@
 // chunk_core.cuh - per-thread arithmetic of the partitioned tridiagonal solve,
 // shared by the strided (y, z) and the contiguous (x) sweep kernels.
 //
-// A thread owns M consecutive rows of one line in registers.  Tables (one set
+// A thread owns M consecutive rows of one line in registers.  Table pointers
+// may point to global memory or to a block's shared-memory copy (plain loads).  Tables (one set
 // per unique line, planes of `pitch` doubles, see heatsim2_b200/plan.py
 // chunk_factors): INV, F, C for the forward part, S, CP for the backward part.
 // `tb` points at the chunk's first row inside plane 0.
@@ -16,7 +17,7 @@ __device__ __forceinline__ double chunk_forward_full(double (&v)[M], const doubl
     const double2 *ci = reinterpret_cast<const double2 *>(tb + HS2_T_INV * pitch);
 #pragma unroll
     for (int t = 0; t < M; t += 2) {
-      const double2 c = __ldg(ci + t / 2);
+      const double2 c = ci[t / 2];
       v[t] *= c.x;
       v[t + 1] *= c.y;
     }
@@ -26,7 +27,7 @@ __device__ __forceinline__ double chunk_forward_full(double (&v)[M], const doubl
     double prev = 0.0;
 #pragma unroll
     for (int t = 0; t < M; t += 2) {
-      const double2 c = __ldg(cf + t / 2);
+      const double2 c = cf[t / 2];
       prev = fma(-c.x, prev, v[t]);
       v[t] = prev;
       prev = fma(-c.y, prev, v[t + 1]);
@@ -37,7 +38,7 @@ __device__ __forceinline__ double chunk_forward_full(double (&v)[M], const doubl
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
   for (int t = 0; t < M; t += 2) {
-    const double2 c = __ldg(cc + t / 2);
+    const double2 c = cc[t / 2];
     a0 = fma(c.x, v[t], a0);
     a1 = fma(c.y, v[t + 1], a1);
   }
@@ -52,9 +53,9 @@ __device__ __forceinline__ double chunk_forward_short(double (&v)[M], const doub
 #pragma unroll
   for (int t = 0; t < M; ++t) {
     if (t < rows) {
-      prev = fma(-__ldg(tb + HS2_T_F * pitch + t), prev, v[t] * __ldg(tb + HS2_T_INV * pitch + t));
+      prev = fma(-tb[HS2_T_F * pitch + t], prev, v[t] * tb[HS2_T_INV * pitch + t]);
       v[t] = prev;
-      yf = fma(__ldg(tb + HS2_T_C * pitch + t), prev, yf);
+      yf = fma(tb[HS2_T_C * pitch + t], prev, yf);
     }
   }
   *last = prev;
@@ -70,7 +71,7 @@ __device__ __forceinline__ void chunk_backward_full(double (&v)[M], const double
     const double2 *cs = reinterpret_cast<const double2 *>(tb + HS2_T_S * pitch);
 #pragma unroll
     for (int t = 0; t < M; t += 2) {
-      const double2 c = __ldg(cs + t / 2);
+      const double2 c = cs[t / 2];
       v[t] = fma(-alpha, c.x, v[t]);
       v[t + 1] = fma(-alpha, c.y, v[t + 1]);
     }
@@ -80,7 +81,7 @@ __device__ __forceinline__ void chunk_backward_full(double (&v)[M], const double
   v[M - 1] = E;
 #pragma unroll
   for (int t = M - 2; t >= 0; t -= 2) {
-    const double2 c = __ldg(cp + t / 2);  // (cp[t], cp[t+1])
+    const double2 c = cp[t / 2];  // (cp[t], cp[t+1])
     if (t + 1 < M - 1) {
       nxt = fma(-c.y, nxt, v[t + 1]);
       v[t + 1] = nxt;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void chunk_backward_short(double (&v)[M], const doubl
   for (int t = M - 1; t >= 0; --t) {
     if (t < rows) {
       if (t < rows - 1)
-        nxt = fma(-__ldg(tb + HS2_T_CP * pitch + t), nxt, fma(-alpha, __ldg(tb + HS2_T_S * pitch + t), v[t]));
+        nxt = fma(-tb[HS2_T_CP * pitch + t], nxt, fma(-alpha, tb[HS2_T_S * pitch + t], v[t]));
       v[t] = nxt;
     }
   }
@@ -116,7 +117,7 @@ __device__ __forceinline__ double chunk_interface(const double *__restrict__ ge,
   const int q0 = max(0, p - band), q1 = min(P - 1, p + band);
 #pragma unroll 4
   for (int q = q0; q <= q1; ++q) {
-    const double2 g = __ldg(g2 + q);
+    const double2 g = g2[q];
     e0 = fma(g.x, Y[(2 * q) * ld + w], e0);
     e1 = fma(g.y, Y[(2 * q + 1) * ld + w], e1);
   }

@@ -122,7 +122,7 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
 // buffer is handed back to the copy engine.  Results are stored straight from
 // registers.  Tensor map: rank 3, dims (n0, n1, n2) = (nx, ny, nz) for the
 // y-sweep and (ny*nx, nz, 1) for the z-sweep, box (W, BR, 1).
-template <int M, int W, bool FINAL>
+template <int M, int W, bool FINAL, bool USE_TMA>
 __global__ void __launch_bounds__(256, 2)
 strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__ data, const double *__restrict__ Tin,
                   double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
@@ -133,6 +133,8 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
   double *Y = tile + (size_t)n_boxes * BR * W;                     // [2P][W]
   double *Es = Y + 2 * P * W;                                      // [P][W]
   uint64_t *bar = reinterpret_cast<uint64_t *>(Es + P * W);
+  double *s_tab = reinterpret_cast<double *>(bar + 2);             // [HS2_T_PLANES][pitch] of one unique line
+  double *s_ge = s_tab + HS2_T_PLANES * pitch;                     // [P][2P]
   const int w = threadIdx.x;
   const int p = threadIdx.y;
   const bool leader = (w == 0 && p == 0);
@@ -141,24 +143,58 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
   const bool full = rows == M;
   const uint32_t tile_bytes = (uint32_t)n_boxes * BR * W * sizeof(double);
 
-  if (leader) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
+  if (USE_TMA) {
+    if (leader) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  // fetch tile t into shared memory: one thread programs the TMA engine, or
+  // (cp.async variant) every thread copies its share in 16-byte pieces
   auto issue = [&](int t) {
     const int group = t / tiles_per_group;
     const int c0 = (t % tiles_per_group) * W;
-    mbar_expect_tx(bar, tile_bytes);
-    for (int b = 0; b < n_boxes; ++b) {
-      if (group_stride)   // y-sweep: (x, row, plane)
-        tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, group);
-      else                // z-sweep: (flattened line, row, 0)
-        tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, 0);
+    if (USE_TMA) {
+      if (!leader) return;
+      mbar_expect_tx(bar, tile_bytes);
+      for (int b = 0; b < n_boxes; ++b) {
+        if (group_stride)   // y-sweep: (x, row, plane)
+          tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, group);
+        else                // z-sweep: (flattened line, row, 0)
+          tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, 0);
+      }
+    } else {
+      const int nthr = W * P;
+      const int tid = p * W + w;
+      const double *src0 = data + (int64_t)group * group_stride + c0;
+      for (int e = tid; e < L * (W / 2); e += nthr) {
+        const int r = e / (W / 2), c = (e % (W / 2)) * 2;
+        const int ok = (c0 + c < lines_per_group) ? 16 : 0;
+        const double *src = src0 + (int64_t)r * stride + (ok ? c : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(tile + (size_t)r * W + c)), "l"(src),
+                     "r"(ok)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   };
   int t = blockIdx.x;
-  if (leader && t < n_tiles) issue(t);
+  if (t < n_tiles) issue(t);
+  HS2_MARK_DECL;
+  // factor tables of the first line's class into shared memory: persistent
+  // blocks re-use them for every tile whose lines are of that class (all of
+  // them on the BASELINE grids); other classes read the global tables
+  uint32_t lid_c = 0xffffffffu;
+  if (t < n_tiles) {
+    lid_c = line_id[(int64_t)(t / tiles_per_group) * lines_per_group + (t % tiles_per_group) * W];
+    const int tid = p * W + w, nthr = W * P;
+    const double *gt = tab + (int64_t)lid_c * HS2_T_PLANES * pitch;
+    for (int e = tid; e < HS2_T_PLANES * pitch; e += nthr) s_tab[e] = gt[e];
+    const double *gg = GE + (int64_t)lid_c * P * 2 * P;
+    for (int e = tid; e < 2 * P * P; e += nthr) s_ge[e] = gg[e];
+  }
+  __syncthreads();
   uint32_t parity = 0;
   for (; t < n_tiles; t += gridDim.x) {
     const int group = t / tiles_per_group;
@@ -167,8 +203,8 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     const int64_t line = (int64_t)group * lines_per_group + (live ? col : 0);
     const int64_t off = (int64_t)group * group_stride + (live ? col : 0) + (int64_t)r0 * stride;
     const uint32_t lid = line_id[line];
-    const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
-    const double *ge = GE + ((int64_t)lid * P + p) * (2 * P);
+    const double *tb = lid == lid_c ? s_tab + r0 : tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
+    const double *ge = lid == lid_c ? s_ge + p * (2 * P) : GE + ((int64_t)lid * P + p) * (2 * P);
     if (FINAL && live && do_prefetch) {
       // warm L2 with the T_in rows this thread adds at the end
       const double *ti = Tin + off;
@@ -176,16 +212,25 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
       for (int q = 0; q < M; q += 4)
         if (q < rows) prefetch_l2(ti + (int64_t)q * stride);
     }
-    mbar_wait(bar, parity);
-    parity ^= 1;
+    HS2_MARK(8);
+    if (USE_TMA) {
+      mbar_wait(bar, parity);
+      parity ^= 1;
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    HS2_MARK(0);
     double v[M];
     {
       const double *mine = tile + (size_t)r0 * W + w;
 #pragma unroll
       for (int q = 0; q < M; ++q) v[q] = (q < rows) ? mine[q * W] : 0.0;
     }
+    HS2_MARK(1);
     __syncthreads();                       // tile buffer is free again
-    if (leader && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+    if (t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+    HS2_MARK(2);
     double yf, last;
     if (full) {
       yf = chunk_forward_full<M>(v, tb, pitch);
@@ -195,15 +240,18 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     }
     Y[(2 * p) * W + w] = yf;
     Y[(2 * p + 1) * W + w] = last;
+    HS2_MARK(3);
     __syncthreads();
     const double E = chunk_interface(ge, Y, P, W, w, p, band);
     Es[p * W + w] = E;
+    HS2_MARK(4);
     __syncthreads();
     const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
     if (full)
       chunk_backward_full<M>(v, tb, pitch, alpha, E);
     else
       chunk_backward_short<M>(v, tb, pitch, rows, alpha, E);
+    HS2_MARK(5);
     if (live) {
       if (FINAL) {
         const double *ti = Tin + off;
@@ -223,6 +271,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
         }
       }
     }
+    HS2_MARK(6);
     // Y/Es are rewritten only after the next tile's first __syncthreads
   }
 }
@@ -240,30 +289,48 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   // row); measured on B200 the tensor copy engine then delivers < half the
   // bandwidth of plain loads (profiles/NOTES_r01.md), so the z-sweep keeps the
   // register-load kernel unless HS2_TMA_Z=1.
-  static const bool enabled_z = getenv("HS2_TMA_Z") != nullptr && getenv("HS2_TMA_Z")[0] == '1';
-  if (group_stride == 0 && !enabled_z) return HS2_OK;
+  // HS2_Z_PREFETCH: 0 = register-load kernel, 1 = cp.async persistent kernel (default), 2 = TMA
+  static const int zmode = getenv("HS2_Z_PREFETCH") ? atoi(getenv("HS2_Z_PREFETCH")) : 1;
+  if (group_stride == 0 && zmode == 0) return HS2_OK;
+  const bool use_tma = group_stride != 0 || zmode == 2;
   static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 1;
   const int BR = L < 256 ? L : 256;
   const int n_boxes = (L + BR - 1) / BR;
-  const size_t smem = ((size_t)n_boxes * BR * W + 3 * (size_t)P * W) * sizeof(double) + 16;
-  if (smem > 110 * 1024) return HS2_OK;
-  CUtensorMap tmap;
-  bool ok;
-  if (group_stride)
-    ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, (uint64_t)n_groups, W, BR, 1);
-  else
-    ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
-  if (!ok) return HS2_OK;
+  const size_t smem = ((size_t)n_boxes * BR * W + 3 * (size_t)P * W + (size_t)HS2_T_PLANES * ax.pitch + 2 * (size_t)P * P) * sizeof(double) + 16;
+  if (smem > 112 * 1024) return HS2_OK;
   const int tiles_per_group = (lines_per_group + W - 1) / W;
   const int64_t n_tiles = (int64_t)n_groups * tiles_per_group;
   if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
-  auto kern = strided_sweep_tma<M, W, FINAL>;
-  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = pl->sm_count * 2;
   if (grid > n_tiles) grid = (int)n_tiles;
   dim3 block(W, P);
-  kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band, stride,
-                                  tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+  static const int carveout_env = getenv("HS2_CARVEOUT") ? atoi(getenv("HS2_CARVEOUT")) : -1;
+  const int carveout = carveout_env >= 0 ? carveout_env : (int)((2 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (use_tma) {
+    bool ok;
+    if (group_stride)
+      ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, (uint64_t)n_groups, W, BR, 1);
+    else
+      ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
+    if (!ok) return HS2_OK;
+    auto kern = strided_sweep_tma<M, W, FINAL, true>;
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
+                                    stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+  } else {
+    // 16-byte cp.async pieces: every row start must be 16-byte aligned
+    if ((lines_per_group & 1) || (stride & 1) || (group_stride & 1) || (reinterpret_cast<uintptr_t>(data) & 15)) return HS2_OK;
+    auto kern = strided_sweep_tma<M, W, FINAL, false>;
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
+                                    stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+  }
   HS2_CUDA_CHECK(cudaGetLastError());
   *done = true;
   return HS2_OK;
@@ -447,3 +514,14 @@ int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cuda
   HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
   return dispatch<true>(p, d.axis[2], W, T, Tout, (int)d.nz, d.ny * d.nx, 1, (int)(d.ny * d.nx), 0, st);
 }
+
+#ifdef HS2_PHASE_TIMING
+extern "C" int hs2_debug_phase_strided(unsigned long long *out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_hs2_phase, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_hs2_phase, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

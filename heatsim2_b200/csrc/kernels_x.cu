@@ -21,6 +21,7 @@
 // per chunk and S_r = 2 mod 16 make both the row-major phases and the
 // chunk-major phase bank-conflict free for 8-byte accesses.
 #include "chunk_core.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -258,6 +259,13 @@ int launch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, con
   HS2_REQUIRE(smem <= (size_t)p->max_smem_optin, "x sweep: tile needs %zu B of shared memory", smem);
   auto kern = sweep_x_kernel<M, CID>;
   if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    // shared memory for the resident blocks only; the rest of the array stays L1 (factor tables, y/x neighbours)
+    static const int carveout_env = getenv("HS2_CARVEOUT_X") ? atoi(getenv("HS2_CARVEOUT_X")) : -1;
+    const int resident = 65536 / (threads * 128) > 0 ? 65536 / (threads * 128) : 1;
+    const int carveout = carveout_env >= 0 ? carveout_env : (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
+  }
   const int tiles_y = (int)((d.ny + R - 1) / R);
   const int64_t blocks = d.nz * tiles_y;
   HS2_REQUIRE(blocks < ((int64_t)1 << 31), "x sweep: too many tiles");

@@ -1,0 +1,103 @@
+"""More GPU parity: tile kernels vs whole-line fallback, u16 class ids, odd
+sizes, long runs, and size-independent properties at full BASELINE sizes."""
+import numpy as np
+import pytest
+
+import problems
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hs():
+    import heatsim2_b200
+    from heatsim2_b200 import _cabi
+    _cabi.lib()
+    return heatsim2_b200
+
+
+def _run_plan(hs, prob, nsteps, flags=0):
+    import torch
+    P, S = hs.setup(*prob["setup_args"])
+    P.plan.flags = flags
+    T = torch.from_numpy(np.array(prob["T0"])).cuda()
+    for it in range(nsteps):
+        T = hs.run_adi_steps(P, S, prob["t0"] + it * prob["dt"], prob["dt"], T,
+                             prob["volumetric_elements"], prob["volumetric"])
+    return T.cpu().numpy(), P.plan
+
+
+@pytest.mark.parametrize("name,kwargs", [
+    ("steelonfoam", dict()),
+    ("uniform_slab", dict(shape=(40, 72, 96))),
+    ("uniform_slab", dict(shape=(33, 34, 50))),       # ragged chunks
+    ("steelonwater", dict(nz=64, ny=48, nx=56)),
+])
+def test_tile_kernels_equal_fallback(hs, name, kwargs):
+    prob = problems.ALL[name](hs, **kwargs)
+    a, plan = _run_plan(hs, prob, 4, flags=0)
+    b, _ = _run_plan(hs, prob, 4, flags=1)             # HS2_FLAG_FORCE_FALLBACK
+    assert plan.launches_per_step == 3
+    assert util.relerr(a, b) <= 1e-13
+
+
+def test_odd_nx_uses_fallback_for_x_and_still_matches_oracle(hs):
+    import adi_oracle
+    prob = problems.uniform_slab(hs, shape=(9, 20, 31))
+    got, plan = _run_plan(hs, prob, 3)
+    assert plan.launches_per_step == 4                  # x: rhs + whole-line solve
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=3)) <= 1e-12
+
+
+def test_more_than_256_classes_u16_ids(hs):
+    """random 3-D material mosaic -> several hundred equation classes"""
+    import adi_oracle
+    rng = np.random.default_rng(5)
+    nz, ny, nx = 12, 14, 16
+    prob = problems.uniform_slab(hs, shape=(nz, ny, nx))
+    args = list(prob["setup_args"])
+    nmat = 6
+    args[10] = tuple((hs.TEMPERATURE_COMPUTE, float(10 + 7 * m), 7.0e3 + 100 * m, 400.0 + 10 * m) for m in range(nmat))
+    me = rng.integers(0, nmat, size=(nz, ny, nx)).astype(np.uint8)
+    args[13] = me
+    prob = dict(prob, setup_args=tuple(args), material_elements=me, materials=args[10])
+    P, S = hs.setup(*prob["setup_args"])
+    assert P.plan.n_classes > 256 and P.plan.class_id.element_size() == 2
+    got, _ = _run_plan(hs, prob, 3)
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=3)) <= 1e-12
+
+
+def test_c2_long_run_vs_oracle(hs):
+    """C2 recipe at 48^3, 300 free-running steps (<= 1e-10)"""
+    import adi_oracle
+    prob = problems.uniform_slab(hs, n=48, nsteps=300)
+    got, _ = _run_plan(hs, prob, 300)
+    assert util.relerr(got, adi_oracle.run(prob)) <= 1e-10
+
+
+def test_full_size_properties_256(hs):
+    """256^3 (BASELINE configs[1] size): energy conservation in the insulated
+    box, linearity of the step, finite output."""
+    import torch
+    prob = problems.uniform_slab(hs, n=256, random_T0=False)
+    P, S = hs.setup(*prob["setup_args"])
+    dt = prob["dt"]
+    ve, vol = prob["volumetric_elements"], prob["volumetric"]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.rand(P.plan.shape, dtype=torch.float64, device="cuda", generator=g)
+    B = torch.rand(P.plan.shape, dtype=torch.float64, device="cuda", generator=g)
+
+    def step(T, t=dt):
+        return hs.run_adi_steps(P, S, t, dt, T, ve, vol)
+    sA, sB = step(A), step(B)
+    # uniform material: sum(T) is conserved by a source-free step
+    assert abs(float(sA.sum() - A.sum())) <= 1e-12 * float(A.sum())
+    lin = step(2.0 * A - 3.0 * B)
+    assert float((lin - (2.0 * sA - 3.0 * sB)).abs().max()) <= 1e-12 * float(lin.abs().max())
+    # the flash deposits exactly 10 kJ/m^2 on layer 0: rho c dz * sum over z = 1e4 per (y,x) column
+    F = hs.run_adi_steps(P, S, 0.0, dt, torch.zeros_like(A), ve, vol)
+    rho, c = prob["materials"][0][2], prob["materials"][0][3]
+    E = float(F.sum()) * rho * c * prob["dz"] / (256 * 256)
+    assert abs(E - 10e3) <= 1e-9 * 10e3
+    assert bool(torch.isfinite(F).all())
