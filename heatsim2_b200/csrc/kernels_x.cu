@@ -46,25 +46,36 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
                const uint8_t *__restrict__ vol, SrcTab st, const double *__restrict__ dense,
                const double *__restrict__ halo_lo, const double *__restrict__ halo_hi,
                const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
-               int nz, int ny, int nx, int pitch, int P, int band, int tiles_y) {
+               int nz, int ny, int nx, int pitch, int P, int band, int tiles_y, int n_tiles, int tab_in_smem) {
   extern __shared__ double sm[];
   const int Sr = row_pitch(P, M);
   double *buf = sm;                       // [R][Sr]
   double *Y = buf + R * Sr;               // [2P][R]
   double *Es = Y + 2 * P * R;             // [P][R]
   double *cfs = Es + P * R;               // [n_classes][8] when coef_in_smem
+  double *s_tab = cfs + (coef_in_smem ? n_classes * HS2_COEF_STRIDE : 0);   // [HS2_T_PLANES][pitch] when tab_in_smem
+  double *s_ge = s_tab + HS2_T_PLANES * pitch;                              // [P][2P]
   HS2_MARK_DECL;
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
-  const int k = blockIdx.x / tiles_y;
-  const int j0 = (blockIdx.x % tiles_y) * R;
   const int64_t plane = (int64_t)ny * nx;
-  const int64_t kbase = (int64_t)k * plane;
-
-  if (coef_in_smem) {
+  // persistent block: class coefficients and the factor tables of the first
+  // line's class are copied to shared memory once and serve every tile
+  uint32_t lid_c = 0xffffffffu;
+  if (coef_in_smem)
     for (int q = tid; q < n_classes * HS2_COEF_STRIDE; q += nthreads) cfs[q] = coef_g[q];
-    __syncthreads();
+  if (tab_in_smem && (int)blockIdx.x < n_tiles) {
+    lid_c = line_id[(int64_t)(blockIdx.x / tiles_y) * ny + (blockIdx.x % tiles_y) * R];
+    const double *gt = tab + (int64_t)lid_c * HS2_T_PLANES * pitch;
+    for (int e = tid; e < HS2_T_PLANES * pitch; e += nthreads) s_tab[e] = gt[e];
+    const double *gg = GE + (int64_t)lid_c * P * 2 * P;
+    for (int e = tid; e < 2 * P * P; e += nthreads) s_ge[e] = gg[e];
   }
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int k = tile / tiles_y;
+  const int j0 = (tile % tiles_y) * R;
+  const int64_t kbase = (int64_t)k * plane;
   const double *coef = coef_in_smem ? cfs : coef_g;
   const int nrows = min(R, ny - j0);
 
@@ -175,8 +186,8 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   const bool full = rows == M;
   const int64_t line = (int64_t)k * ny + j0 + (r < nrows ? r : 0);
   const uint32_t lid = line_id[line];
-  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + c0;
-  const double *ge = GE + ((int64_t)lid * P + pc) * (2 * P);
+  const double *tb = lid == lid_c ? s_tab + c0 : tab + ((int64_t)lid * HS2_T_PLANES) * pitch + c0;
+  const double *ge = lid == lid_c ? s_ge + pc * (2 * P) : GE + ((int64_t)lid * P + pc) * (2 * P);
   double *mine = buf + r * Sr + pc * (M + 1);
   double v[M];
   double yf, last;
@@ -229,6 +240,8 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
       if (r < nrows) *reinterpret_cast<double2 *>(Wk + (int64_t)r * nx + i) = o[r];
   }
   HS2_MARK(8);
+  __syncthreads();                        // buf, Y, Es are rewritten by the next tile
+  }
 }
 
 int make_src_tab(const hs2_source *src, SrcTab *st) {
@@ -254,26 +267,34 @@ int launch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, con
   const int threads = R * P;
   const int Sr = row_pitch(P, M);
   const int coef_in_smem = d.n_classes <= 256 ? 1 : 0;
-  const size_t smem = ((size_t)R * Sr + 3 * (size_t)P * R + (coef_in_smem ? (size_t)d.n_classes * HS2_COEF_STRIDE : 0)) *
-                      sizeof(double);
+  const size_t base_smem = ((size_t)R * Sr + 3 * (size_t)P * R + (coef_in_smem ? (size_t)d.n_classes * HS2_COEF_STRIDE : 0)) *
+                           sizeof(double);
+  const size_t tab_smem = ((size_t)HS2_T_PLANES * ax.pitch + 2 * (size_t)P * P) * sizeof(double);
+  static const int tabs_env = getenv("HS2_X_TABS_SMEM") ? atoi(getenv("HS2_X_TABS_SMEM")) : 0;   // measured: 4 resident blocks beat 3 with tables in smem
+  const int tab_in_smem = (tabs_env && base_smem + tab_smem <= 72 * 1024) ? 1 : 0;
+  const size_t smem = base_smem + (tab_in_smem ? tab_smem : 0);
   HS2_REQUIRE(smem <= (size_t)p->max_smem_optin, "x sweep: tile needs %zu B of shared memory", smem);
   auto kern = sweep_x_kernel<M, CID>;
   if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int resident = 65536 / (threads * 128) > 0 ? 65536 / (threads * 128) : 1;
+  while (resident > 1 && resident * (smem + 1024) > 227 * 1024) --resident;
   {
-    // shared memory for the resident blocks only; the rest of the array stays L1 (factor tables, y/x neighbours)
+    // shared memory for the resident blocks only; the rest of the array stays L1 (y/x neighbour re-reads)
     static const int carveout_env = getenv("HS2_CARVEOUT_X") ? atoi(getenv("HS2_CARVEOUT_X")) : -1;
-    const int resident = 65536 / (threads * 128) > 0 ? 65536 / (threads * 128) : 1;
     const int carveout = carveout_env >= 0 ? carveout_env : (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
   }
   const int tiles_y = (int)((d.ny + R - 1) / R);
-  const int64_t blocks = d.nz * tiles_y;
-  HS2_REQUIRE(blocks < ((int64_t)1 << 31), "x sweep: too many tiles");
+  const int64_t n_tiles = d.nz * tiles_y;
+  HS2_REQUIRE(n_tiles < ((int64_t)1 << 31), "x sweep: too many tiles");
+  int64_t blocks = (int64_t)p->sm_count * resident;
+  if (blocks > n_tiles) blocks = n_tiles;
   const uint8_t *vol = (src && tabsrc.n) ? src->d_vol_elements : nullptr;
   const double *dense = src ? src->d_dense : nullptr;
   kern<<<(unsigned)blocks, threads, smem, st>>>(T, W, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes, coef_in_smem,
                                                  vol, tabsrc, dense, halo_lo, halo_hi, ax.d_line_id, ax.d_tab, ax.d_GE,
-                                                 (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, ax.band, tiles_y);
+                                                 (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, ax.band, tiles_y, (int)n_tiles,
+                                                 tab_in_smem);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }
