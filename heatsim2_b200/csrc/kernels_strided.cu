@@ -205,11 +205,11 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     const uint32_t lid = line_id[line];
     const double *tb = lid == lid_c ? s_tab + r0 : tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
     const double *ge = lid == lid_c ? s_ge + p * (2 * P) : GE + ((int64_t)lid * P + p) * (2 * P);
-    if (FINAL && live && do_prefetch) {
-      // warm L2 with the T_in rows this thread adds at the end
+    if (FINAL && live && do_prefetch && (w & 3) == 0) {
+      // warm L2 with the T_in rows this tile adds at the end (one lane per 32-byte sector)
       const double *ti = Tin + off;
 #pragma unroll
-      for (int q = 0; q < M; q += 4)
+      for (int q = 0; q < M; ++q)
         if (q < rows) prefetch_l2(ti + (int64_t)q * stride);
     }
     HS2_MARK(8);
@@ -254,13 +254,17 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     HS2_MARK(5);
     if (live) {
       if (FINAL) {
+        // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
         const double *ti = Tin + off;
         double *to = Tout + off;
 #pragma unroll
-        for (int q = 0; q < M; ++q) {
-          if (q < rows) *to = *ti + v[q];
-          ti += stride;
-          to += stride;
+        for (int g = 0; g < M; g += 8) {
+          double tin[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tin[q] = (g + q < rows) ? ti[(int64_t)(g + q) * stride] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (g + q < rows) to[(int64_t)(g + q) * stride] = tin[q] + v[g + q];
         }
       } else {
         double *dst = data + off;

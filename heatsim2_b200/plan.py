@@ -63,7 +63,7 @@ def thomas_factors(lo, dg, hi):
     return out
 
 
-def choose_chunk(L):
+def choose_chunk(L, axis=None):
     """Rows per chunk M and chunk count P for a line of length L.  The kernels
     hold M doubles per thread in registers and run P*W threads per tile
     (W = 16 or 8 adjacent lines): M=8 with up to 16 chunks, M=16 with up to 32,
@@ -75,6 +75,8 @@ def choose_chunk(L):
         return 0, 0
     if L > 256:
         pref = int(os.environ.get("HS2_CHUNK", "32"))
+        if axis == 0:
+            pref = int(os.environ.get("HS2_CHUNK_X", str(pref)))
         for M, P in valid:
             if M == pref:
                 return M, P
@@ -255,7 +257,7 @@ class AdiPlan(object):
                 n_chunks = dg.shape[1] // rows_per_chunk
                 self.line_lu.append(np.zeros((dg.shape[0], 1, _cabi.HS2_LU_STRIDE)))    # whole-line path unused
             else:
-                rows_per_chunk, n_chunks = choose_chunk(dg.shape[1])
+                rows_per_chunk, n_chunks = choose_chunk(dg.shape[1], axis)
                 self.line_lu.append(thomas_factors(lo, dg, hi))
             self.chunk.append((rows_per_chunk, n_chunks))
             self.chunk_tabs.append(chunk_factors(lo, dg, hi, rows_per_chunk) if rows_per_chunk else None)

@@ -28,7 +28,7 @@ for it in range(n):
 torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 16)()
 lib.hs2_debug_phase(out, 0)
-nblocks = grid * ((grid + 7) // 8) * n
+nblocks = grid * ((grid + 7) // 8) * n   # tiles
 names = ["phase1 rhs", "sync", "load+fwd", "sync", "interface", "sync", "bwd+sts", "sync", "phase3 store"]
 tot = sum(out[:9])
 for i, nm in enumerate(names):
