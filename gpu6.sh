@@ -1,3 +1,8 @@
-nvidia-smi -L
-timeout 900 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -5
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -3
+for PL in 2 1; do
+HS2_DIST_PIPELINE=$PL timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('pipeline $PL: ms/step',d['ms_per_step'],'value',d['value']/1e9,'G',d['comm'])
+"
+done

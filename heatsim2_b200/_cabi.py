@@ -58,8 +58,9 @@ PROTOTYPES = {
     "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_y": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_z": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hs2_sweep_z_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hs2_sweep_z_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hs2_sweep_z_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p]),
+    "hs2_sweep_z_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                            ctypes.c_int64, c_void_p]),
     "hs2_tridiag_scratch_bytes": (ctypes.c_int64, [ctypes.c_int64]),
     "hs2_tridiag_lu": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hs2_tridiag_solve": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

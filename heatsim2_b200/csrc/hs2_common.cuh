@@ -65,6 +65,7 @@ int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cuda
 bool hs2_tile_x_supported(const hs2_plan *p);
 int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                      const double *halo_hi, cudaStream_t st);
-int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, cudaStream_t st);
+int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
+              int64_t n_lines, cudaStream_t st);
 int hs2_tile_sweep_x_march(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                            const double *halo_hi, cudaStream_t st, bool *done);

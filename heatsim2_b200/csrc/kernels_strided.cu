@@ -396,22 +396,23 @@ int dispatch(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double
 // back-substitutes.  No transpose of the field is ever needed.
 template <int M, int W>
 __global__ void __launch_bounds__(256, 2)
-z_forward(double *__restrict__ data, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
-          double *__restrict__ Yloc, int pitch, int row0, int64_t stride, int n_lines) {
+z_forward(const double *__restrict__ data, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
+          double *__restrict__ Yloc, int pitch, int row0, int64_t stride, int line0, int n_lines) {
   const int w = threadIdx.x, p = threadIdx.y;
-  const int col = blockIdx.x * W + w;
-  if (col >= n_lines) return;
+  const int rel = blockIdx.x * W + w;          // line within the processed range
+  if (rel >= n_lines) return;
+  const int col = line0 + rel;
   const uint32_t lid = line_id[col];
   const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
-  double *ptr = data + col + (int64_t)p * M * stride;
+  const double *ptr = data + col + (int64_t)p * M * stride;
   double v[M];
 #pragma unroll
   for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
+  // the eliminated chunk is NOT written back: z_backward repeats the (cheap)
+  // forward elimination from the same input instead of re-reading 8 B/cell
   const double yf = chunk_forward_full<M>(v, tb, pitch);
-#pragma unroll
-  for (int t = 0; t < M; ++t) ptr[(int64_t)t * stride] = v[t];
-  Yloc[(int64_t)(2 * p) * n_lines + col] = yf;
-  Yloc[(int64_t)(2 * p + 1) * n_lines + col] = v[M - 1];
+  Yloc[(int64_t)(2 * p) * n_lines + rel] = yf;
+  Yloc[(int64_t)(2 * p + 1) * n_lines + rel] = v[M - 1];
 }
 
 template <int M, int W>
@@ -419,10 +420,11 @@ __global__ void __launch_bounds__(256, 2)
 z_backward(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
            const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
            const double *__restrict__ Yall, int pitch, int row0, int P_glob, int chunk0, int band, int64_t stride,
-           int n_lines) {
+           int line0, int n_lines) {
   const int w = threadIdx.x, p = threadIdx.y;
-  const int col = blockIdx.x * W + w;
-  if (col >= n_lines) return;
+  const int rel = blockIdx.x * W + w;
+  if (rel >= n_lines) return;
+  const int col = line0 + rel;
   const uint32_t lid = line_id[col];
   const int pg = chunk0 + p;
   const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
@@ -437,63 +439,73 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
     const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
     for (int q = q0; q <= q1; ++q) {
       const double2 g = __ldg(reinterpret_cast<const double2 *>(ge) + q);
-      E = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + col], E);
-      E = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + col], E);
+      E = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + rel], E);
+      E = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + rel], E);
     }
     if (pg > 0) {
       const double *gm = ge - 2 * P_glob;
       const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
       for (int q = a0; q <= a1; ++q) {
         const double2 g = __ldg(reinterpret_cast<const double2 *>(gm) + q);
-        alpha = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + col], alpha);
-        alpha = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + col], alpha);
+        alpha = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + rel], alpha);
+        alpha = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + rel], alpha);
       }
     }
   }
+  chunk_forward_full<M>(v, tb, pitch);       // same arithmetic as z_forward
   chunk_backward_full<M>(v, tb, pitch, alpha, E);
+  // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
 #pragma unroll
-  for (int t = 0; t < M; ++t) Tout[off + (int64_t)t * stride] = Tin[off + (int64_t)t * stride] + v[t];
+  for (int g = 0; g < M; g += 8) {
+    double tin[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tin[q] = Tin[off + (int64_t)(g + q) * stride];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(g + q) * stride] = tin[q] + v[g + q];
+  }
 }
 
 template <int M>
-int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, cudaStream_t st) {
+int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
+                 int n_lines, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const hs2_axis_tables &ax = d.axis[2];
   const int P_loc = (int)(d.nz / M);
   const int W = P_loc * 16 <= 256 ? 16 : 8;
   HS2_REQUIRE(P_loc * W <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
-  const int n_lines = (int)(d.ny * d.nx);
   const int blocks = (n_lines + W - 1) / W;
   const int row0 = d.z_chunk0 * M;
   dim3 block(W, P_loc);
   if (phase == 0) {
     if (W == 16)
-      z_forward<M, 16><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, n_lines);
+      z_forward<M, 16><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, line0, n_lines);
     else
-      z_forward<M, 8><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, n_lines);
+      z_forward<M, 8><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, line0, n_lines);
   } else {
     if (W == 16)
       z_backward<M, 16><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
-                                                  d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, n_lines);
+                                                  d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines);
     else
       z_backward<M, 8><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
-                                                 d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, n_lines);
+                                                 d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines);
   }
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }
 
-int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, cudaStream_t st) {
+int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
+              int64_t n_lines, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const int M = d.axis[2].chunk;
   HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
   HS2_REQUIRE((M == 8 || M == 16 || M == 32) && d.nz % M == 0 && d.axis[2].d_tab && d.axis[2].d_GE,
               "distributed z sweep needs chunk tables and nz (%lld) divisible by the chunk size (%d)", (long long)d.nz, M);
   HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
+  HS2_REQUIRE(line0 >= 0 && n_lines > 0 && line0 + n_lines <= d.ny * d.nx, "distributed z sweep: bad line range");
   switch (M) {
-    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, st);
-    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, st);
-    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, st);
+    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
+    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
+    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
   }
 }
 

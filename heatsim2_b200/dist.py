@@ -21,6 +21,7 @@ The result differs from the single-GPU path only by rounding (same chunked
 algorithm; a single GPU applies the interface operator inside one kernel).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -29,7 +30,7 @@ import torch.distributed as dist
 from . import _cabi
 from . import alternatingdirection_c_pyx as alternatingdirection
 from . import crank_nicolson
-from .plan import AdiPlan
+from .plan import AdiPlan, interface_band
 
 
 def slab_range(nz, rank, world):
@@ -53,6 +54,11 @@ class DistPlan(object):
         self.k0 = plan.slab["k0"]
         self.chunk = plan.chunk[2][0]
         self.p_loc = plan.shape[0] // self.chunk
+        # slabs whose interface values this slab needs: chunk p uses chunks p-1-band .. p+band
+        self.band = interface_band(plan.chunk_tabs[2][1])
+        self.hops = -(-(self.band + 1) // self.p_loc)
+        self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "2"))
+        self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
         self._bufs = {}
 
     # ------------------------------------------------------------- buffers
@@ -77,12 +83,14 @@ class DistPlan(object):
     def _k_sweep_y(self, work):
         _cabi.check(_cabi.lib().hs2_sweep_y(self.plan._handle, work.data_ptr(), self._stream(work)))
 
-    def _k_z_forward(self, work, Y):
-        _cabi.check(_cabi.lib().hs2_sweep_z_forward(self.plan._handle, work.data_ptr(), Y.data_ptr(), self._stream(work)))
+    def _k_z_forward(self, work, Y, line0, n_lines):
+        _cabi.check(_cabi.lib().hs2_sweep_z_forward(self.plan._handle, work.data_ptr(), Y.data_ptr(), line0, n_lines,
+                                                    self._stream(work)))
 
-    def _k_z_backward(self, T_in, T_out, work, Yall):
+    def _k_z_backward(self, T_in, T_out, work, Yall, line0, n_lines):
         _cabi.check(_cabi.lib().hs2_sweep_z_backward(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(),
-                                                     work.data_ptr(), Yall.data_ptr(), self._stream(work)))
+                                                     work.data_ptr(), Yall.data_ptr(), line0, n_lines,
+                                                     self._stream(work)))
 
     def _stream(self, t):
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
@@ -110,6 +118,32 @@ class DistPlan(object):
                 req.wait()
         return halo_lo, halo_hi
 
+    def _line_ranges(self, n_lines):
+        """Split the z-lines into `pipeline` ranges (multiples of 16 lines)."""
+        parts = max(1, min(self.pipeline, n_lines // self.min_lines))
+        step = -(-n_lines // parts)
+        step = -(-step // 16) * 16
+        return [(l0, min(step, n_lines - l0)) for l0 in range(0, n_lines, step)]
+
+    def _exchange_interface(self, Yall, own):
+        """Deliver this slab's interface values to every slab that needs them
+        and receive theirs into the matching slices of ``Yall``.  Chunk p needs
+        the chunks p-1-band .. p+band, i.e. slabs within ``hops`` of its own;
+        when that is (almost) everybody a single all-gather is used instead.
+        Returns the outstanding requests."""
+        if self.world == 1:
+            return []
+        if 2 * self.hops >= self.world - 1:
+            return [dist.all_gather_into_tensor(Yall, own, group=self.group, async_op=True)]
+        rows = 2 * self.p_loc
+        ops = []
+        for d in range(1, self.hops + 1):
+            for r in (self.rank - d, self.rank + d):
+                if 0 <= r < self.world:
+                    ops.append(dist.P2POp(dist.isend, own, self._peer(r), self.group))
+                    ops.append(dist.P2POp(dist.irecv, Yall[r * rows:(r + 1) * rows], self._peer(r), self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
     # ----------------------------------------------------------------- step
     def step_device(self, T_in, T_out, t, dt, volumetric_elements, volumetric):
         """One time step of this rank's slab (tensors [nz/W, ny, nx] float64 on
@@ -126,11 +160,20 @@ class DistPlan(object):
         work = self._buf("work", self.shape, T_in)
         self._k_sweep_x(T_in, work, src, keep, halo_lo, halo_hi)
         self._k_sweep_y(work)
-        Y = self._buf("Y", (2 * self.p_loc, ny * nx), T_in)
-        Yall = self._buf("Yall", (self.world * 2 * self.p_loc, ny * nx), T_in)
-        self._k_z_forward(work, Y)
-        dist.all_gather_into_tensor(Yall, Y, group=self.group)
-        self._k_z_backward(T_in, T_out, work, Yall)
+        # z-sweep, pipelined over ranges of lines: while the interface values of
+        # one range travel over NVLink the next range is being eliminated
+        n_lines = ny * nx
+        ranges = self._line_ranges(n_lines)
+        pending = []
+        for (l0, nl) in ranges:
+            Yall = self._buf("Yall%d" % l0, (self.world * 2 * self.p_loc, nl), T_in)
+            own = Yall[self.rank * 2 * self.p_loc:(self.rank + 1) * 2 * self.p_loc]
+            self._k_z_forward(work, own, l0, nl)
+            pending.append((l0, nl, Yall, self._exchange_interface(Yall, own)))
+        for (l0, nl, Yall, reqs) in pending:
+            for req in reqs:
+                req.wait()
+            self._k_z_backward(T_in, T_out, work, Yall, l0, nl)
         if keep is not None and len(keep) > 1 and T_in.is_cuda:
             torch.cuda.current_stream(T_in.device).synchronize()
         return T_out
@@ -148,8 +191,12 @@ class DistPlan(object):
     def comm_bytes_per_step(self):
         ny, nx = self.shape[1:]
         halo = ny * nx * 8 * ((self.rank > 0) + (self.rank < self.world - 1))
-        gather = 2 * self.p_loc * ny * nx * 8 * (self.world - 1)
-        return {"halo_send": halo, "allgather_send": gather}
+        if 2 * self.hops >= self.world - 1:
+            peers = self.world - 1
+        else:
+            peers = sum(1 for d in range(1, self.hops + 1) for r in (self.rank - d, self.rank + d) if 0 <= r < self.world)
+        return {"halo_send": halo, "interface_send": 2 * self.p_loc * ny * nx * 8 * peers,
+                "interface_mode": "all-gather" if 2 * self.hops >= self.world - 1 else "%d-hop neighbours" % self.hops}
 
 
 def setup(z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric,

@@ -104,7 +104,8 @@ def run(args, shape, workload_name):
                              "peak_source": peak_src,
                              "note": "algorithmic 56 B/cell-update; the slab z-sweep actually moves %d B/cell" % bytes_cell},
                 "comm": {"halo_bytes_per_rank_per_step": comm["halo_send"],
-                         "allgather_bytes_sent_per_rank_per_step": comm["allgather_send"],
+                         "interface_bytes_sent_per_rank_per_step": comm["interface_send"],
+                         "interface_exchange": comm["interface_mode"], "pipeline_ranges": len(dplan._line_ranges(shape[1] * shape[2])),
                          "backend": "NCCL %s over NVLink" % ".".join(str(v) for v in torch.cuda.nccl.version())},
                 "cpu_baseline": None,
                 "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_global * 8,

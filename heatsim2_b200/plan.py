@@ -40,7 +40,8 @@ def _line_view(a3, axis):
 def slab_chunk(nz_local):
     """Chunk size of the distributed z-solve: the largest of 32/16/8 that
     divides the slab thickness with at most 32 chunks per slab."""
-    for M in (32, 16, 8):
+    forced = int(os.environ.get("HS2_SLAB_CHUNK", "0"))
+    for M in ((forced,) if forced in (8, 16, 32) else (32, 16, 8)):
         if nz_local % M == 0 and nz_local // M <= 32:
             return M
     raise NotImplementedError("slab thickness %d must be a multiple of 8 (at most 32 chunks of 8/16/32 planes)" % nz_local)

@@ -147,17 +147,21 @@ int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream);
 int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out,
                 double *d_work, void *stream);
 
-/* z-sweep of a slab plan, in two halves around one collective (there is no
- * reference counterpart: heatsim2 is single-process).
- *   forward : eliminate the local chunks of d_work in place and write their
- *             (y_first, y_last) pairs to d_Y [2*nz/chunk][ny*nx]
- *   <caller all-gathers d_Y of all slabs, in slab order, into d_Yall
- *    [2*z_chunks_global][ny*nx] - NCCL all-gather over NVLink>
- *   backward: interface values from d_Yall, back-substitution,
- *             d_T_out = d_T_in + increment                                    */
-int hs2_sweep_z_forward(hs2_plan *plan, double *d_work, double *d_Y, void *stream);
+/* z-sweep of a slab plan, in two halves around one exchange (there is no
+ * reference counterpart: heatsim2 is single-process).  Both calls work on the
+ * z-lines [line0, line0 + n_lines) (line = j*nx + i), so that a caller can
+ * pipeline: while one range of lines is being exchanged the next one is solved.
+ *   forward : eliminate the local chunks of d_work (d_work is left untouched)
+ *             and write their (y_first, y_last) pairs to d_Y [2*nz/chunk][n_lines]
+ *   <caller delivers d_Y of every slab that lies within the interface band,
+ *    in slab order, into d_Yall [2*z_chunks_global][n_lines] - NCCL over NVLink>
+ *   backward: repeat the elimination, interface values from d_Yall,
+ *             back-substitution, d_T_out = d_T_in + increment               */
+int hs2_sweep_z_forward(hs2_plan *plan, double *d_work, double *d_Y,
+                        int64_t line0, int64_t n_lines, void *stream);
 int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out,
-                         double *d_work, const double *d_Yall, void *stream);
+                         double *d_work, const double *d_Yall,
+                         int64_t line0, int64_t n_lines, void *stream);
 
 /* Drop-ins for heatsim2/tridiag.pyx on device arrays.
  * hs2_tridiag_lu    = tridiaglu   (:9-43):  A[n][3] -> L[n][3], U[n][3]

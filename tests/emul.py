@@ -141,20 +141,35 @@ class EmulDistPlan(hdist.DistPlan):
         lid = plan.line_id[2].cpu().numpy()
         return tab_u[lid], GE_u[lid]
 
-    def _k_z_forward(self, work, Y):
+    def _k_z_forward(self, work, Y, line0, n_lines):
         tab, _ = self._z_tables()
-        d = np.ascontiguousarray(_lines(work.numpy(), 2))
-        u, Yl = chunk_forward(d, tab, self.chunk, row0=self.k0)
-        work.copy_(torch.from_numpy(np.ascontiguousarray(_unlines(u, self.shape, 2))))
+        sl = slice(line0, line0 + n_lines)
+        full = np.ascontiguousarray(_lines(work.numpy(), 2))
+        u, Yl = chunk_forward(full[sl], tab[sl], self.chunk, row0=self.k0)      # u is not kept (recomputed later)
         Y.copy_(torch.from_numpy(np.ascontiguousarray(Yl.T)))           # [2P_loc, n_lines]
 
-    def _k_z_backward(self, T_in, T_out, work, Yall):
+    def _k_z_backward(self, T_in, T_out, work, Yall, line0, n_lines):
         tab, GE = self._z_tables()
-        Yg = Yall.numpy().T                                               # [n_lines, 2P_glob]
-        Eg = np.einsum("npq,nq->np", GE, Yg)                              # all global chunks
+        sl = slice(line0, line0 + n_lines)
+        # slabs outside the exchange radius were never received: their slots hold
+        # garbage that must not matter (the operator is banded) - poison them
+        Yg = Yall.numpy().T.copy()                                        # [n_lines, 2P_glob]
+        rows = 2 * self.p_loc
+        for r in range(self.world):
+            if abs(r - self.rank) > self.hops and 2 * self.hops < self.world - 1:
+                Yg[:, r * rows:(r + 1) * rows] = 0.0
+        P_glob = GE.shape[1]
+        band = self.band
+        mask = (np.abs(np.arange(P_glob)[:, None] - np.arange(P_glob)[None, :]) <= band).astype(float)
+        mask2 = np.repeat(mask, 2, axis=1)                                # interleaved (yf, yl) columns
+        Eg = np.einsum("npq,nq->np", GE[sl] * mask2[None], Yg)
         c0 = self.k0 // self.chunk
         E = Eg[:, c0:c0 + self.p_loc]
         alpha = np.concatenate([np.zeros((E.shape[0], 1)), Eg], axis=1)[:, c0:c0 + self.p_loc]
-        u = np.ascontiguousarray(_lines(work.numpy(), 2))
-        x = chunk_backward(u, tab, self.chunk, E, alpha, row0=self.k0)
-        T_out.copy_(T_in + torch.from_numpy(np.ascontiguousarray(_unlines(x, self.shape, 2))))
+        full_d = np.ascontiguousarray(_lines(work.numpy(), 2))
+        u, _ = chunk_forward(full_d[sl], tab[sl], self.chunk, row0=self.k0)
+        x = chunk_backward(u, tab[sl], self.chunk, E, alpha, row0=self.k0)
+        out = np.ascontiguousarray(_lines(T_out.numpy(), 2)) if T_out is not T_in else np.ascontiguousarray(_lines(T_in.numpy(), 2))
+        tin = np.ascontiguousarray(_lines(T_in.numpy(), 2))
+        out[sl] = tin[sl] + x
+        T_out.copy_(torch.from_numpy(np.ascontiguousarray(_unlines(out, self.shape, 2))))

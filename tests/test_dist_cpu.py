@@ -25,7 +25,8 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, kwargs, nsteps, q):
+def _worker(rank, world, port, name, kwargs, nsteps, q, env=None):
+    os.environ.update(env or {})
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -39,23 +40,26 @@ def _worker(rank, world, port, name, kwargs, nsteps, q):
         ve = prob["volumetric_elements"][k0:k1]
         for it in range(nsteps):
             T = hs.run_adi_steps(P, S, prob["t0"] + it * prob["dt"], prob["dt"], T, ve, prob["volumetric"])
-        q.put((rank, k0, k1, T.numpy()))
+        q.put((rank, k0, k1, T.numpy(), P.plan.comm_bytes_per_step()["interface_mode"], len(P.plan._line_ranges(T.shape[1] * T.shape[2]))))
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, name, kwargs, nsteps):
+def _run(world, name, kwargs, nsteps, env=None, info=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, env)) for r in range(world)]
     for p in procs:
         p.start()
     parts = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    parts.sort()
+    parts.sort(key=lambda t: t[0])
+    if info is not None:
+        info["mode"] = parts[0][4]
+        info["ranges"] = parts[0][5]
     return np.concatenate([p[3] for p in parts], axis=0)
 
 
@@ -71,6 +75,18 @@ def test_slabs_match_oracle(world, name, kwargs):
     got = _run(world, name, kwargs, nsteps)
     prob = problems.ALL[name](hs, **kwargs)
     want = adi_oracle.run(prob, nsteps=nsteps)
+    assert util.relerr(got, want) <= 1e-12
+
+
+def test_neighbour_exchange_and_pipelining():
+    """weakly coupled z-lines (thin plies): the interface band is a few chunks, so
+    slabs exchange with their nearest neighbours only, in two pipelined line ranges"""
+    import heatsim2_b200 as hs
+    kwargs = dict(nz=96, ny=12, nx=16, ply=8)
+    info = {}
+    got = _run(6, "composite", kwargs, 3, env={"HS2_SLAB_CHUNK": "8", "HS2_DIST_MIN_LINES": "64"}, info=info)
+    assert info["mode"] in ("1-hop neighbours", "2-hop neighbours") and info["ranges"] == 2
+    want = adi_oracle.run(problems.composite(hs, **kwargs), nsteps=3)
     assert util.relerr(got, want) <= 1e-12
 
 
