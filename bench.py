@@ -210,6 +210,8 @@ def run_b200_single(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     shape = grid_for(1, args.grid)
+    if args.shape:
+        shape = tuple(int(v) for v in args.shape.split(","))
     t0 = time.perf_counter()
     prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
     P, S = hs.setup(*prob["setup_args"])
@@ -321,6 +323,7 @@ def main():
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default="", help="nz,ny,nx override of the single-GPU grid (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

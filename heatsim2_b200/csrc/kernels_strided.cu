@@ -122,8 +122,8 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
 // buffer is handed back to the copy engine.  Results are stored straight from
 // registers.  Tensor map: rank 3, dims (n0, n1, n2) = (nx, ny, nz) for the
 // y-sweep and (ny*nx, nz, 1) for the z-sweep, box (W, BR, 1).
-template <int M, int W, bool FINAL, bool USE_TMA>
-__global__ void __launch_bounds__(256, 2)
+template <int M, int W, bool FINAL, bool USE_TMA, bool BIG>
+__global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 2)
 strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__ data, const double *__restrict__ Tin,
                   double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
                   const double *__restrict__ GE, int L, int pitch, int P, int band, int64_t stride, int tiles_per_group,
@@ -286,7 +286,11 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   *done = false;
   const int P = ax.n_chunks;
   constexpr int W = 16;
-  if (P * W > 256) return HS2_OK;
+  // up to 16 chunks: 256-thread blocks, two per SM; up to 32 chunks (lines of
+  // 513..1024 rows): one 512-thread block per SM with the whole 128 KB tile
+  if (M < 32 && P * W > 256) return HS2_OK;
+  if (P * W > 512) return HS2_OK;
+  const bool big = P * W > 256;
   static const bool disabled = getenv("HS2_NO_TMA") != nullptr && getenv("HS2_NO_TMA")[0] == '1';
   if (disabled) return HS2_OK;
   // z-lines put consecutive rows 8*ny*nx bytes apart (a different 2 MB page per
@@ -301,7 +305,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   const int BR = L < 256 ? L : 256;
   const int n_boxes = (L + BR - 1) / BR;
   const size_t smem = ((size_t)n_boxes * BR * W + 3 * (size_t)P * W + (size_t)HS2_T_PLANES * ax.pitch + 2 * (size_t)P * P) * sizeof(double) + 16;
-  if (smem > 112 * 1024) return HS2_OK;
+  if (smem > (big ? 224u : 112u) * 1024) return HS2_OK;
   const int tiles_per_group = (lines_per_group + W - 1) / W;
   const int64_t n_tiles = (int64_t)n_groups * tiles_per_group;
   if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
@@ -309,7 +313,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   if (grid > n_tiles) grid = (int)n_tiles;
   dim3 block(W, P);
   static const int carveout_env = getenv("HS2_CARVEOUT") ? atoi(getenv("HS2_CARVEOUT")) : -1;
-  const int carveout = carveout_env >= 0 ? carveout_env : (int)((2 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  const int carveout = carveout_env >= 0 ? carveout_env : (int)(((big ? 1 : 2) * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (use_tma) {
@@ -319,19 +323,19 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
     else
       ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
     if (!ok) return HS2_OK;
-    auto kern = strided_sweep_tma<M, W, FINAL, true>;
+    auto kern = big ? strided_sweep_tma<M, W, FINAL, true, (M >= 32)> : strided_sweep_tma<M, W, FINAL, true, false>;
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
     kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
   } else {
     // 16-byte cp.async pieces: every row start must be 16-byte aligned
     if ((lines_per_group & 1) || (stride & 1) || (group_stride & 1) || (reinterpret_cast<uintptr_t>(data) & 15)) return HS2_OK;
-    auto kern = strided_sweep_tma<M, W, FINAL, false>;
+    auto kern = big ? strided_sweep_tma<M, W, FINAL, false, (M >= 32)> : strided_sweep_tma<M, W, FINAL, false, false>;
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
     kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
   }

@@ -57,7 +57,8 @@ class DistPlan(object):
         # slabs whose interface values this slab needs: chunk p uses chunks p-1-band .. p+band
         self.band = interface_band(plan.chunk_tabs[2][1])
         self.hops = -(-(self.band + 1) // self.p_loc)
-        self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "2"))
+        # pipelining pays once the exchange is large (measured: no gain at 2 ranks)
+        self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "1" if self.world <= 2 else "2"))
         self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
         self._bufs = {}
 
