@@ -92,3 +92,4 @@ from . import crank_nicolson                            # noqa: E402
 
 setup = crank_nicolson.setup
 run_adi_steps = alternatingdirection_c_pyx.run_adi_steps
+run_adi_steps_n = alternatingdirection_c_pyx.run_adi_steps_n      # extension: device-resident loop + on-device observation

@@ -260,3 +260,54 @@ def run_adi_steps(ADI_params, ADI_steps, t, dt, Tarray, volumetric_elements, vol
     if plan is None:
         raise RuntimeError("ADI_params carries no plan; it must come from heatsim2_b200.setup()")
     return plan.run_step(t, dt, Tarray, volumetric_elements, volumetric, out=out)
+
+
+def run_adi_steps_n(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, volumetric, nsteps,
+                    probes=None, surface_dz=None, every=1):
+    """``nsteps`` time steps with the field resident on the device and
+    observation on the device (extension; the reference's demos copy the whole
+    field to the host every step and index it there, demos/steelonfoam.py:132-143).
+
+    Step n (0-based) is taken at time ``t0 + n*dt``, like the demos' loops.
+    ``probes``: list of (k, j, i) cells whose temperature is recorded after
+    every ``every``-th step; ``surface_dz``: when given, the insulated z-min
+    surface temperature (``surface_temperature.insulating_z_min_surface_temperature``)
+    is evaluated on the device at the same instants.  Only the recorded values
+    cross PCIe, once, at the end.
+
+    Returns ``(T_final, record)`` with ``record = {"step": [...], "probes":
+    ndarray [n_rec, n_probes], "surface": ndarray [n_rec, ny, nx]}`` (keys present
+    when requested).  ``Tarray`` may be numpy (copied in once; result numpy) or a
+    CUDA tensor (result CUDA tensor)."""
+    import torch
+    from . import surface_temperature as st
+    plan = ADI_params.plan
+    if plan is None:
+        raise RuntimeError("ADI_params carries no plan; it must come from heatsim2_b200.setup()")
+    was_numpy = not isinstance(Tarray, torch.Tensor)
+    if was_numpy:
+        plan.ensure_device()
+        cur = torch.from_numpy(np.ascontiguousarray(Tarray, dtype=np.float64)).to(plan._dev)
+    else:
+        cur = Tarray.contiguous().clone()
+    nxt = torch.empty_like(cur)
+    rec_steps, rec_probe, rec_surf = [], [], []
+    idx = None
+    if probes:
+        pk, pj, pi = (torch.tensor([p[a] for p in probes], device=cur.device, dtype=torch.long) for a in range(3))
+        idx = (pk, pj, pi)
+    for n in range(int(nsteps)):
+        run_adi_steps(ADI_params, ADI_steps, t0 + n * dt, dt, cur, volumetric_elements, volumetric, out=nxt)
+        cur, nxt = nxt, cur
+        if (n + 1) % every == 0:
+            rec_steps.append(n + 1)
+            if idx is not None:
+                rec_probe.append(cur[idx])
+            if surface_dz is not None:
+                rec_surf.append(st.insulating_z_min_surface_temperature(cur, surface_dz))
+    record = {"step": rec_steps}
+    if idx is not None:
+        record["probes"] = torch.stack(rec_probe).cpu().numpy() if rec_probe else np.zeros((0, len(probes)))
+    if surface_dz is not None:
+        record["surface"] = torch.stack(rec_surf).cpu().numpy() if rec_surf else np.zeros((0,) + tuple(cur.shape[1:]))
+    return (cur.cpu().numpy() if was_numpy else cur), record

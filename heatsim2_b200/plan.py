@@ -68,20 +68,22 @@ def choose_chunk(L, axis=None):
     """Rows per chunk M and chunk count P for a line of length L.  The kernels
     hold M doubles per thread in registers and run P*W threads per tile
     (W = 16 or 8 adjacent lines): M=8 with up to 16 chunks, M=16 with up to 32,
-    M=32 with up to 32.  The smallest valid M is taken, except that lines
-    longer than 256 rows use HS2_CHUNK (default 32) when it is valid.
-    (0, 0): too long for the register-tile kernels (whole-line fallback)."""
+    M=32 with up to 32.  Measured on B200, longer chunks win as long as a line
+    still has >= 4 of them, so the largest valid M <= HS2_CHUNK (default 32;
+    HS2_CHUNK_X for the x axis) with at least 4 chunks is taken, else the
+    largest valid M.  (0, 0): too long for the register-tile kernels
+    (whole-line fallback)."""
     valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
     if not valid:
         return 0, 0
-    if L > 256:
-        pref = int(os.environ.get("HS2_CHUNK", "32"))
-        if axis == 0:
-            pref = int(os.environ.get("HS2_CHUNK_X", str(pref)))
-        for M, P in valid:
-            if M == pref:
-                return M, P
-    return valid[0]
+    pref = int(os.environ.get("HS2_CHUNK", "32"))
+    if axis == 0:
+        pref = int(os.environ.get("HS2_CHUNK_X", str(pref)))
+    good = [(M, P) for M, P in valid if M <= pref and P >= 4]
+    if good:
+        return good[-1]
+    small = [(M, P) for M, P in valid if M <= pref]
+    return small[0] if small else valid[0]
 
 
 T_INV, T_F, T_C, T_S, T_CP, T_PLANES = 0, 1, 2, 3, 4, 5

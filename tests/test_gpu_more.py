@@ -101,3 +101,18 @@ def test_full_size_properties_256(hs):
     E = float(F.sum()) * rho * c * prob["dz"] / (256 * 256)
     assert abs(E - 10e3) <= 1e-9 * 10e3
     assert bool(torch.isfinite(F).all())
+
+
+def test_device_resident_loop_with_observation(hs):
+    """run_adi_steps_n: probes and surface temperature recorded on the device
+    equal the step-by-step host loop of demos/steelonfoam.py; C1 golden probes."""
+    z, meta = util.load_golden("c1_steelonfoam")
+    prob = problems.steelonfoam(hs, nsteps=100)
+    P, S = hs.setup(*prob["setup_args"])
+    Tn, rec = hs.run_adi_steps_n(P, S, prob["t0"], prob["dt"], prob["T0"], prob["volumetric_elements"],
+                                 prob["volumetric"], 100, probes=prob["probes"], surface_dz=prob["dz"], every=1)
+    assert isinstance(Tn, np.ndarray) and rec["probes"].shape == (100, 2) and rec["surface"].shape == (100, 40, 48)
+    assert util.relerr(rec["probes"], z["probe_hist"][:100]) <= 1e-10
+    assert util.relerr(Tn, z["T_100"]) <= 1e-10
+    want_surface = hs.surface_temperature.insulating_z_min_surface_temperature(Tn, prob["dz"])
+    assert util.relerr(rec["surface"][-1], want_surface) <= 1e-14

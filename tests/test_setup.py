@@ -279,8 +279,10 @@ def test_chunk_tables_solve_lines(L):
 def test_choose_chunk_limits():
     from heatsim2_b200.plan import choose_chunk
     assert choose_chunk(48) == (8, 6)
-    assert choose_chunk(256) == (16, 16)
-    assert choose_chunk(512) in ((16, 32), (32, 16))
+    assert choose_chunk(128) == (32, 4)
+    assert choose_chunk(256) == (32, 8)
+    assert choose_chunk(512) == (32, 16)
+    assert choose_chunk(20) == (8, 3)
     assert choose_chunk(1024) == (32, 32)
     assert choose_chunk(1025) == (0, 0)
 
