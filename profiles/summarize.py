@@ -15,12 +15,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def short(name):
-    for key, lab in (("sweep_x_kernel", "sweep_x_kernel (x: RHS + solve)"), ("strided_sweep_tma", "strided_sweep_tma (y)"),
-                     ("strided_sweep<", "strided_sweep (z)"), ("z_forward", "z_forward"), ("z_backward", "z_backward"),
+    import re
+    m = re.search(r"strided_sweep(_tma)?<([^>]*)>", name)
+    if m:
+        args = [a.replace("(int)", "").replace("(bool)", "").strip() for a in m.group(2).split(",")]
+        final = args[2] in ("1", "true")
+        if m.group(1):
+            how = "TMA prefetch" if args[3] in ("1", "true") else "cp.async prefetch"
+            return "strided_sweep_tma (%s, persistent, %s)" % ("z" if final else "y", how)
+        return "strided_sweep (%s, register loads)" % ("z" if final else "y")
+    for key, lab in (("sweep_x_kernel", "sweep_x_kernel (x: RHS + solve)"), ("sweep_x_march", "sweep_x_march (x, z-marching)"),
+                     ("z_forward", "z_forward (slab)"), ("z_backward", "z_backward (slab)"),
                      ("rhs_kernel", "rhs_kernel (fallback)"), ("thomas_kernel", "thomas_kernel (fallback)")):
         if key in name:
-            if key == "strided_sweep<" and ", 0>" in name.replace("(bool)", ""):
-                return "strided_sweep (y, register loads)"
             return lab
     return name.split("(")[0][-60:]
 
@@ -34,7 +41,7 @@ def launches(path):
         a[0] += 1
         a[1] += float(r[-1])
     tot = sum(a[1] for a in agg.values())
-    print("# ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n")
+    print("# ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of `python bench.py --steps 4 --warmup 3 --no-cpu-baseline` (kernels of this library only: `-k regex:sweep|thomas_kernel|rhs_kernel|z_forward|z_backward`)\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
     print("| kernel | launches | total ms | mean us | share |\n|---|---|---|---|---|")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
