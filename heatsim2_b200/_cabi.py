@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -20,7 +20,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 class AxisTables(ctypes.Structure):
     _fields_ = [
         ("d_line_id", c_void_p), ("d_lu", c_void_p),
-        ("d_tab", c_void_p), ("d_GE", c_void_p),
+        ("d_tab", c_void_p), ("d_GE", c_void_p), ("d_tab_il", c_void_p),
         ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
         ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]

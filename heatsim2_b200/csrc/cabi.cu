@@ -66,6 +66,8 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
                 const double *d_halo_hi, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
+  if (hs2_tile_xf_supported(plan))
+    return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
   if (hs2_tile_x_supported(plan))
     return hs2_tile_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
   return hs2_v1_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);

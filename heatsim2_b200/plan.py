@@ -153,6 +153,19 @@ def chunk_factors(lo, dg, hi, M):
     return tab, GE
 
 
+def interleave_chunks(tab, L, M, P):
+    """Chunk-interleaved copy of the factor tables for the x-sweep kernel
+    (kernels_xf.cu): [nu, planes, M/2, P, 2] with rows 2t, 2t+1 of chunk p at
+    [.., t, p, :].  A warp of that kernel works on four neighbouring chunks of
+    eight lines; this order puts the four table entries it loads together in one
+    64-byte segment.  Rows past the end of the line: 1/piv = 1, everything else 0."""
+    nu = tab.shape[0]
+    full = np.zeros((nu, T_PLANES, P * M))
+    full[:, T_INV, :] = 1.0
+    full[:, :, :L] = tab[:, :, :L]
+    return np.ascontiguousarray(full.reshape(nu, T_PLANES, P, M // 2, 2).transpose(0, 1, 3, 2, 4))
+
+
 def interface_band(GE, tol=1e-16):
     """Half-width, in chunks, outside which every entry of every GE row is
     below ``tol`` times the row maximum (the interface operator decays
@@ -310,6 +323,10 @@ class AdiPlan(object):
                 ax.d_tab, ax.d_GE = (t.data_ptr() for t in self.d_chunk[a])
                 ax.pitch = self.d_chunk[a][0].shape[2]
                 ax.band = interface_band(self.chunk_tabs[a][1])
+                if a == 0:
+                    M, P = self.chunk[0]
+                    self.d_tab_il = torch.from_numpy(interleave_chunks(self.chunk_tabs[0][0], self.shape[2], M, P)).to(dev)
+                    ax.d_tab_il = self.d_tab_il.data_ptr()
         desc.device = dev.index
         desc.flags = self.flags
         if self.slab is not None:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS2_ABI_VERSION 1
+#define HS2_ABI_VERSION 2
 
 #define HS2_OK 0
 #define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
@@ -55,6 +55,12 @@ extern "C" {
  *                                          (chunk-local factorisation)
  *   d_GE  [n_unique][n_chunks][2*n_chunks] row of the inverse interface
  *                                          operator giving the chunk's last x
+ *   d_tab_il [n_unique][HS2_T_PLANES][chunk/2][n_chunks][2]  (x axis only, may
+ *                                          be NULL) the same planes with the
+ *                                          chunks interleaved: rows 2t, 2t+1 of
+ *                                          chunk p at ((plane*chunk/2 + t)*
+ *                                          n_chunks + p)*2; rows past the end
+ *                                          of the line hold 1/piv = 1, rest 0
  * chunk == 0 means the tables are absent and the whole-line path is used.   */
 #define HS2_T_INV 0
 #define HS2_T_F 1
@@ -68,6 +74,7 @@ typedef struct hs2_axis_tables {
   const double *d_lu;        /* device [n_unique][L][HS2_LU_STRIDE]            */
   const double *d_tab;
   const double *d_GE;
+  const double *d_tab_il;
   int32_t n_unique;
   int32_t chunk;
   int32_t n_chunks;
