@@ -21,6 +21,7 @@
 // per chunk and S_r = 2 mod 16 make both the row-major phases and the
 // chunk-major phase bank-conflict free for 8-byte accesses.
 #include "chunk_core.cuh"
+#include "tma_util.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -46,7 +47,7 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
                const uint8_t *__restrict__ vol, SrcTab st, const double *__restrict__ dense,
                const double *__restrict__ halo_lo, const double *__restrict__ halo_hi,
                const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
-               int nz, int ny, int nx, int pitch, int P, int band, int tiles_y, int n_tiles, int tab_in_smem) {
+               int nz, int ny, int nx, int pitch, int P, int band, int tiles_y, int n_tiles, int tab_in_smem, int pf) {
   extern __shared__ double sm[];
   const int Sr = row_pitch(P, M);
   double *buf = sm;                       // [R][Sr]
@@ -78,6 +79,19 @@ sweep_x_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CI
   const int64_t kbase = (int64_t)k * plane;
   const double *coef = coef_in_smem ? cfs : coef_g;
   const int nrows = min(R, ny - j0);
+  if (pf) {
+    // the only rows of a tile nobody has touched yet are its z+ neighbours:
+    // ask L2 for those of this block's NEXT tile now (128-byte lines)
+    const int tn = tile + gridDim.x;
+    if (tn < n_tiles) {
+      const int kn = tn / tiles_y, jn = (tn % tiles_y) * R;
+      if (kn + 1 < nz) {
+        const double *nxt = T + (int64_t)(kn + 1) * plane + (int64_t)jn * nx;
+        const int n_el = min(R, ny - jn) * nx;
+        for (int e = tid * 16; e < n_el; e += nthreads * 16) prefetch_l2(nxt + e);
+      }
+    }
+  }
 
   // ------------------------------------------------ phase 1: right hand side
   // z neighbours: the planes below/above, the neighbouring slab's halo plane,
@@ -291,10 +305,11 @@ int launch_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, con
   if (blocks > n_tiles) blocks = n_tiles;
   const uint8_t *vol = (src && tabsrc.n) ? src->d_vol_elements : nullptr;
   const double *dense = src ? src->d_dense : nullptr;
+  static const int pf = getenv("HS2_X_PREFETCH") ? atoi(getenv("HS2_X_PREFETCH")) : 0;   // measured on B200: the prefetch costs 0.05 ms
   kern<<<(unsigned)blocks, threads, smem, st>>>(T, W, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes, coef_in_smem,
                                                  vol, tabsrc, dense, halo_lo, halo_hi, ax.d_line_id, ax.d_tab, ax.d_GE,
                                                  (int)d.nz, (int)d.ny, (int)d.nx, ax.pitch, P, ax.band, tiles_y, (int)n_tiles,
-                                                 tab_in_smem);
+                                                 tab_in_smem, pf);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }
