@@ -61,6 +61,16 @@ PROTOTYPES = {
     "hs2_sweep_z_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p]),
     "hs2_sweep_z_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64,
                                             ctypes.c_int64, c_void_p]),
+    "hs2_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_void_p), c_void_p]),
+    "hs2_peer_open": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "hs2_peer_close": (ctypes.c_int, [c_void_p]),
+    "hs2_peer_free": (ctypes.c_int, [c_void_p]),
+    "hs2_sweep_z_forward_push": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64),
+                                                c_void_p]),
+    "hs2_flag_signal": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_uint64, c_void_p]),
+    "hs2_flag_wait": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_uint64, ctypes.c_double,
+                                     c_void_p, c_void_p]),
+    "hs2_copy_async": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p]),
     "hs2_tridiag_scratch_bytes": (ctypes.c_int64, [ctypes.c_int64]),
     "hs2_tridiag_lu": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hs2_tridiag_solve": (ctypes.c_int, [ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -123,3 +123,102 @@ __device__ __forceinline__ double chunk_interface(const double *__restrict__ ge,
   }
   return e0 + e1;
 }
+
+// ---------------------------------------------------------------------------
+// Accessor-based variants.  Measured on B200 (profiles/micro/tabsrc.cu): the
+// per-row factors are broadcast loads (all lines of a warp that sit in the same
+// chunk read the same address), and a 16-byte shared load costs the data pipe
+// ~8 cycles per warp whatever the addresses are, while 8-byte shared loads of
+// one or two distinct addresses cost 1-2.  The solve went from 1.5 to 4.3-7.0
+// row-updates/cycle/SM.  So the tables are read with explicit 8-byte
+// ld.shared.f64 (inline PTX keeps the compiler from re-fusing neighbours into
+// one 16-byte load) when the block has them in shared memory, and with scalar
+// __ldg otherwise.
+struct TabShared {
+  uint32_t a;        // shared-window byte address of plane 0 at this thread's first row
+  uint32_t pitch_b;  // bytes between planes
+  __device__ __forceinline__ uint32_t plane(int pl) const { return a + pl * pitch_b; }
+  __device__ __forceinline__ static double ld(uint32_t q, int t) {
+    double x;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(q + 8u * (uint32_t)t));
+    return x;
+  }
+};
+
+struct TabGlobal {
+  const double *b;  // plane 0 at this thread's first row
+  int pitch;        // doubles between planes
+  __device__ __forceinline__ const double *plane(int pl) const { return b + (int64_t)pl * pitch; }
+  __device__ __forceinline__ static double ld(const double *q, int t) { return __ldg(q + t); }
+};
+
+// forward elimination of a chunk of `rows` <= M rows (rows == M: no guards);
+// returns y_first, *last = y_last, v = chunk-local forward solution
+template <int M, bool FULL, class TAB>
+__device__ __forceinline__ double chunk_fwd(double (&v)[M], const TAB &tb, int rows, double *last) {
+  {
+    const auto q = tb.plane(HS2_T_INV);
+#pragma unroll
+    for (int t = 0; t < M; ++t)
+      if (FULL || t < rows) v[t] *= TAB::ld(q, t);
+  }
+  double prev = 0.0;
+  {
+    const auto q = tb.plane(HS2_T_F);
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+      if (FULL || t < rows) {
+        prev = fma(-TAB::ld(q, t), prev, v[t]);
+        v[t] = prev;
+      }
+    }
+  }
+  *last = prev;
+  double a0 = 0.0, a1 = 0.0;
+  {
+    const auto q = tb.plane(HS2_T_C);
+#pragma unroll
+    for (int t = 0; t < M; t += 2) {
+      if (FULL || t < rows) a0 = fma(TAB::ld(q, t), v[t], a0);
+      if (FULL || t + 1 < rows) a1 = fma(TAB::ld(q, t + 1), v[t + 1], a1);
+    }
+  }
+  return a0 + a1;
+}
+
+// back substitution given alpha (true x just before the chunk) and E (true x of
+// the chunk's last row); v becomes the solution
+template <int M, bool FULL, class TAB>
+__device__ __forceinline__ void chunk_bwd(double (&v)[M], const TAB &tb, int rows, double alpha, double E) {
+  {
+    const auto q = tb.plane(HS2_T_S);
+#pragma unroll
+    for (int t = 0; t < M; ++t)
+      if (FULL || t < rows) v[t] = fma(-alpha, TAB::ld(q, t), v[t]);
+  }
+  const auto q = tb.plane(HS2_T_CP);
+  double nxt = E;
+#pragma unroll
+  for (int t = M - 1; t >= 0; --t) {
+    if (FULL) {
+      if (t < M - 1) nxt = fma(-TAB::ld(q, t), nxt, v[t]);
+      v[t] = nxt;
+    } else if (t < rows) {
+      if (t < rows - 1) nxt = fma(-TAB::ld(q, t), nxt, v[t]);
+      v[t] = nxt;
+    }
+  }
+}
+
+// E_p from the interleaved (yf, yl) values of the line's chunks, 8-byte loads
+// of the inverse interface operator row (shared window address or global)
+__device__ __forceinline__ double chunk_interface_s(uint32_t ge_s, const double *Y, int P, int ld, int w, int p, int band) {
+  double e0 = 0.0, e1 = 0.0;
+  const int q0 = max(0, p - band), q1 = min(P - 1, p + band);
+#pragma unroll 4
+  for (int q = q0; q <= q1; ++q) {
+    e0 = fma(TabShared::ld(ge_s, 2 * q), Y[(2 * q) * ld + w], e0);
+    e1 = fma(TabShared::ld(ge_s, 2 * q + 1), Y[(2 * q + 1) * ld + w], e1);
+  }
+  return e0 + e1;
+}

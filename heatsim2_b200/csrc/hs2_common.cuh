@@ -66,7 +66,7 @@ bool hs2_tile_x_supported(const hs2_plan *p);
 int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                      const double *halo_hi, cudaStream_t st);
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
-              int64_t n_lines, cudaStream_t st);
+              int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st);
 // kernels_xf.cu - x sweep with the explicit x-term folded into the solve (default)
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,

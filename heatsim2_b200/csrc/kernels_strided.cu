@@ -231,6 +231,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     __syncthreads();                       // tile buffer is free again
     if (t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
     HS2_MARK(2);
+    // (16-byte table loads: the 8-byte variant of chunk_core.cuh measured 6 % slower here)
     double yf, last;
     if (full) {
       yf = chunk_forward_full<M>(v, tb, pitch);
@@ -398,107 +399,191 @@ int dispatch(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double
 // doubles per chunk per line over NCCL; phase 2 (z_backward) applies the rows
 // p-1 and p of the GLOBAL inverse interface operator to get alpha and E and
 // back-substitutes.  No transpose of the field is ever needed.
+struct ZPeers {  // where this slab's (y_first, y_last) rows go in the peers' interface buffers
+  int n;
+  double *y[HS2_MAX_Z_PEERS];
+};
+
+// Both kernels: block = (W lines, P_loc chunks, G line groups) = 256 threads,
+// persistent over groups of G tiles.  The factor-table rows of this slab and the
+// P_loc+1 rows of the global inverse interface operator it needs are copied to
+// shared memory once per block (class of the block's first line; lines of
+// another class read global memory) and read with 8-byte broadcast loads.
 template <int M, int W>
 __global__ void __launch_bounds__(256, 2)
 z_forward(const double *__restrict__ data, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
-          double *__restrict__ Yloc, int pitch, int row0, int64_t stride, int line0, int n_lines) {
-  const int w = threadIdx.x, p = threadIdx.y;
-  const int rel = blockIdx.x * W + w;          // line within the processed range
-  if (rel >= n_lines) return;
-  const int col = line0 + rel;
-  const uint32_t lid = line_id[col];
-  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
-  const double *ptr = data + col + (int64_t)p * M * stride;
-  double v[M];
+          double *__restrict__ Yloc, int pitch, int row0, int nz_loc, int64_t stride, int line0, int n_lines, int n_tiles,
+          ZPeers peers) {
+  extern __shared__ __align__(16) double zsm[];
+  double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
+  const int w = threadIdx.x, p = threadIdx.y, g = threadIdx.z, G = blockDim.z;
+  const int tid = (g * blockDim.y + p) * W + w, nthr = W * blockDim.y * G;
+  int tile = blockIdx.x * G;
+  if (tile >= n_tiles) return;
+  const uint32_t lid_c = line_id[line0 + tile * W];
+  for (int e = tid; e < HS2_T_PLANES * nz_loc; e += nthr)
+    s_tab[e] = tab[((int64_t)lid_c * HS2_T_PLANES + e / nz_loc) * pitch + row0 + e % nz_loc];
+  __syncthreads();
+  TabShared ts;
+  ts.a = smem_u32(s_tab + p * M);
+  ts.pitch_b = (uint32_t)nz_loc * 8u;
+  for (; tile < n_tiles; tile += gridDim.x * G) {
+    const int rel = (tile + g) * W + w;          // line within the processed range
+    if (tile + g >= n_tiles || rel >= n_lines) continue;
+    const int col = line0 + rel;
+    const uint32_t lid = line_id[col];
+    const double *ptr = data + col + (int64_t)p * M * stride;
+    double v[M];
 #pragma unroll
-  for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
-  // the eliminated chunk is NOT written back: z_backward repeats the (cheap)
-  // forward elimination from the same input instead of re-reading 8 B/cell
-  const double yf = chunk_forward_full<M>(v, tb, pitch);
-  Yloc[(int64_t)(2 * p) * n_lines + rel] = yf;
-  Yloc[(int64_t)(2 * p + 1) * n_lines + rel] = v[M - 1];
+    for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
+    // the eliminated chunk is NOT written back: z_backward repeats the (cheap)
+    // forward elimination from the same input instead of re-reading 8 B/cell
+    double yf, last;
+    if (lid == lid_c) {
+      yf = chunk_fwd<M, true>(v, ts, M, &last);
+    } else {
+      TabGlobal tg;
+      tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+      tg.pitch = pitch;
+      yf = chunk_fwd<M, true>(v, tg, M, &last);
+    }
+    Yloc[(int64_t)(2 * p) * n_lines + rel] = yf;
+    Yloc[(int64_t)(2 * p + 1) * n_lines + rel] = last;
+    // the same two values straight into the memory of the slabs that need them (NVLink stores)
+#pragma unroll
+    for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
+      if (q < peers.n) {
+        peers.y[q][(int64_t)(2 * p) * n_lines + rel] = yf;
+        peers.y[q][(int64_t)(2 * p + 1) * n_lines + rel] = last;
+      }
+    }
+  }
 }
 
 template <int M, int W>
 __global__ void __launch_bounds__(256, 2)
 z_backward(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
            const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
-           const double *__restrict__ Yall, int pitch, int row0, int P_glob, int chunk0, int band, int64_t stride,
-           int line0, int n_lines) {
-  const int w = threadIdx.x, p = threadIdx.y;
-  const int rel = blockIdx.x * W + w;
-  if (rel >= n_lines) return;
-  const int col = line0 + rel;
-  const uint32_t lid = line_id[col];
+           const double *__restrict__ Yall, int pitch, int row0, int nz_loc, int P_glob, int chunk0, int band,
+           int64_t stride, int line0, int n_lines, int n_tiles) {
+  extern __shared__ __align__(16) double zsm[];
+  double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
+  double *s_ge = s_tab + HS2_T_PLANES * nz_loc;          // [P_loc + 1][2 P_glob]: rows chunk0-1 .. chunk0+P_loc-1
+  const int w = threadIdx.x, p = threadIdx.y, g = threadIdx.z, G = blockDim.z;
+  const int P_loc = blockDim.y;
+  const int tid = (g * P_loc + p) * W + w, nthr = W * P_loc * G;
+  int tile = blockIdx.x * G;
+  if (tile >= n_tiles) return;
+  const uint32_t lid_c = line_id[line0 + tile * W];
+  for (int e = tid; e < HS2_T_PLANES * nz_loc; e += nthr)
+    s_tab[e] = tab[((int64_t)lid_c * HS2_T_PLANES + e / nz_loc) * pitch + row0 + e % nz_loc];
+  for (int e = tid; e < (P_loc + 1) * 2 * P_glob; e += nthr) {
+    const int row = chunk0 - 1 + e / (2 * P_glob);
+    s_ge[e] = row >= 0 ? GE[((int64_t)lid_c * P_glob + row) * (2 * P_glob) + e % (2 * P_glob)] : 0.0;
+  }
+  __syncthreads();
   const int pg = chunk0 + p;
-  const double *tb = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
-  const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
-  const int64_t off = col + (int64_t)p * M * stride;
-  double v[M];
+  TabShared ts;
+  ts.a = smem_u32(s_tab + p * M);
+  ts.pitch_b = (uint32_t)nz_loc * 8u;
+  const uint32_t ge_s = smem_u32(s_ge + (p + 1) * 2 * P_glob);   // row pg; row pg-1 sits just before it
+  for (; tile < n_tiles; tile += gridDim.x * G) {
+    const int rel = (tile + g) * W + w;
+    if (tile + g >= n_tiles || rel >= n_lines) continue;
+    const int col = line0 + rel;
+    const uint32_t lid = line_id[col];
+    const bool tab_s = lid == lid_c;
+    const int64_t off = col + (int64_t)p * M * stride;
+    double v[M];
 #pragma unroll
-  for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
-  // rows pg (-> E) and pg-1 (-> alpha) of the inverse interface operator
-  double E = 0.0, alpha = 0.0;
-  {
-    const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
-    for (int q = q0; q <= q1; ++q) {
-      const double2 g = __ldg(reinterpret_cast<const double2 *>(ge) + q);
-      E = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + rel], E);
-      E = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + rel], E);
-    }
-    if (pg > 0) {
-      const double *gm = ge - 2 * P_glob;
-      const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
-      for (int q = a0; q <= a1; ++q) {
-        const double2 g = __ldg(reinterpret_cast<const double2 *>(gm) + q);
-        alpha = fma(g.x, Yall[(int64_t)(2 * q) * n_lines + rel], alpha);
-        alpha = fma(g.y, Yall[(int64_t)(2 * q + 1) * n_lines + rel], alpha);
+    for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
+    // rows pg (-> E) and pg-1 (-> alpha) of the inverse interface operator
+    double E = 0.0, alpha = 0.0;
+    {
+      const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
+      const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
+      for (int q = q0; q <= q1; ++q) {
+        const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
+        const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
+        E = fma(g0, Yall[(int64_t)(2 * q) * n_lines + rel], E);
+        E = fma(g1, Yall[(int64_t)(2 * q + 1) * n_lines + rel], E);
+      }
+      if (pg > 0) {
+        const double *gm = ge - 2 * P_glob;
+        const uint32_t gm_s = ge_s - 16u * (uint32_t)P_glob;
+        const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
+        for (int q = a0; q <= a1; ++q) {
+          const double g0 = tab_s ? TabShared::ld(gm_s, 2 * q) : __ldg(gm + 2 * q);
+          const double g1 = tab_s ? TabShared::ld(gm_s, 2 * q + 1) : __ldg(gm + 2 * q + 1);
+          alpha = fma(g0, Yall[(int64_t)(2 * q) * n_lines + rel], alpha);
+          alpha = fma(g1, Yall[(int64_t)(2 * q + 1) * n_lines + rel], alpha);
+        }
       }
     }
-  }
-  chunk_forward_full<M>(v, tb, pitch);       // same arithmetic as z_forward
-  chunk_backward_full<M>(v, tb, pitch, alpha, E);
-  // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
+    double last;
+    if (tab_s) {
+      chunk_fwd<M, true>(v, ts, M, &last);       // same arithmetic as z_forward
+      chunk_bwd<M, true>(v, ts, M, alpha, E);
+    } else {
+      TabGlobal tg;
+      tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+      tg.pitch = pitch;
+      chunk_fwd<M, true>(v, tg, M, &last);
+      chunk_bwd<M, true>(v, tg, M, alpha, E);
+    }
+    // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
 #pragma unroll
-  for (int g = 0; g < M; g += 8) {
-    double tin[8];
+    for (int gb = 0; gb < M; gb += 8) {
+      double tin[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) tin[q] = Tin[off + (int64_t)(g + q) * stride];
+      for (int q = 0; q < 8; ++q) tin[q] = Tin[off + (int64_t)(gb + q) * stride];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(g + q) * stride] = tin[q] + v[g + q];
+      for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[q] + v[gb + q];
+    }
   }
 }
 
-template <int M>
-int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
-                 int n_lines, cudaStream_t st) {
+template <int M, int W>
+int launch_zdist_w(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
+                   int n_lines, const ZPeers &peers, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const hs2_axis_tables &ax = d.axis[2];
   const int P_loc = (int)(d.nz / M);
-  const int W = P_loc * 16 <= 256 ? 16 : 8;
-  HS2_REQUIRE(P_loc * W <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
-  const int blocks = (n_lines + W - 1) / W;
+  const int G = 256 / (W * P_loc) > 0 ? 256 / (W * P_loc) : 1;
+  const int n_tiles = (n_lines + W - 1) / W;
   const int row0 = d.z_chunk0 * M;
-  dim3 block(W, P_loc);
+  const int nz_loc = (int)d.nz;
+  const size_t smem = ((size_t)HS2_T_PLANES * nz_loc + (phase ? (size_t)(P_loc + 1) * 2 * d.z_chunks_global : 0)) * sizeof(double);
+  HS2_REQUIRE(smem <= 100 * 1024, "distributed z sweep: tables need %zu B of shared memory", smem);
+  int blocks = pl->sm_count * 2;
+  if (blocks > (n_tiles + G - 1) / G) blocks = (n_tiles + G - 1) / G;
+  dim3 block(W, P_loc, G);
   if (phase == 0) {
-    if (W == 16)
-      z_forward<M, 16><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, line0, n_lines);
-    else
-      z_forward<M, 8><<<blocks, block, 0, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, d.ny * d.nx, line0, n_lines);
+    auto kern = z_forward<M, W>;
+    if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, block, smem, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, nz_loc, d.ny * d.nx, line0, n_lines,
+                                      n_tiles, peers);
   } else {
-    if (W == 16)
-      z_backward<M, 16><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
-                                                  d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines);
-    else
-      z_backward<M, 8><<<blocks, block, 0, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0,
-                                                 d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines);
+    auto kern = z_backward<M, W>;
+    if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0, nz_loc,
+                                      d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines, n_tiles);
   }
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }
 
+template <int M>
+int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
+                 int n_lines, const ZPeers &peers, cudaStream_t st) {
+  const int P_loc = (int)(pl->d.nz / M);
+  HS2_REQUIRE(P_loc * 8 <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
+  if (P_loc * 16 <= 256) return launch_zdist_w<M, 16>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, st);
+  return launch_zdist_w<M, 8>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, st);
+}
+
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
-              int64_t n_lines, cudaStream_t st) {
+              int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const int M = d.axis[2].chunk;
   HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
@@ -506,10 +591,15 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
               "distributed z sweep needs chunk tables and nz (%lld) divisible by the chunk size (%d)", (long long)d.nz, M);
   HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
   HS2_REQUIRE(line0 >= 0 && n_lines > 0 && line0 + n_lines <= d.ny * d.nx, "distributed z sweep: bad line range");
+  HS2_REQUIRE(n_peers >= 0 && n_peers <= HS2_MAX_Z_PEERS && (n_peers == 0 || peer_y), "distributed z sweep: %d peers (max %d)",
+              n_peers, HS2_MAX_Z_PEERS);
+  ZPeers peers;
+  peers.n = n_peers;
+  for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;
   switch (M) {
-    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
-    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
-    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, st);
+    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
+    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
+    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
   }
 }
 

@@ -19,6 +19,16 @@ Per time step
 
 The result differs from the single-GPU path only by rounding (same chunked
 algorithm; a single GPU applies the interface operator inside one kernel).
+
+Two transports for the two exchanges:
+  * peer memory (default on CUDA, ``PeerExchange``): every rank maps a mailbox of
+    its neighbours (CUDA IPC over NVLink).  The z_forward kernel stores its
+    interface values straight into the mailboxes of the slabs that need them,
+    halo planes are copied there with cudaMemcpyAsync, and the GPUs order each
+    other with flags in peer memory (stream-ordered signal / bounded wait
+    kernels).  No collective call, no host synchronisation, one stream.
+  * NCCL send/recv or all-gather (``HS2_DIST_P2P=0``, CPU/gloo tests, or when the
+    interface band reaches more slabs than a kernel can address).
 """
 import ctypes
 import os
@@ -41,6 +51,79 @@ def slab_range(nz, rank, world):
     return rank * h, (rank + 1) * h
 
 
+class PeerExchange(object):
+    """Mailbox of one rank in its own device memory, mapped by the ranks that
+    write to it.  Layout (bytes):
+      [0, 4096)   flags: Y-ready flag of source slab s at 8*s; halo-ready flags at
+                  2048 (from the slab below) and 2056 (from above); status word at 3072
+      halo_lo, halo_hi            one [ny][nx] plane each
+      Y[parity]                   (2*hops+1) slab slots of 2*p_loc rows x n_lines doubles;
+                                  slot i holds the rows of slab rank-hops+i
+    Flags carry the step number (monotone), so nothing is ever reset."""
+
+    HEADER = 4096
+    OFF_FLAG_H_LO, OFF_FLAG_H_HI, OFF_STATUS = 2048, 2056, 3072
+
+    def __init__(self, rank, world, hops, p_loc, ny, nx, group, device):
+        self.rank, self.world, self.hops = rank, world, hops
+        self.lib = _cabi.lib()
+        self.peers = [r for d in range(1, hops + 1) for r in (rank - d, rank + d) if 0 <= r < world]
+        if len(self.peers) > 6 or world > 240:
+            raise NotImplementedError("interface band reaches %d slabs" % len(self.peers))
+        self.n_lines = ny * nx
+        self.plane_bytes = self.n_lines * 8
+        self.slab_bytes = 2 * p_loc * self.n_lines * 8
+        self.y_bytes = (2 * hops + 1) * self.slab_bytes
+        self.off_halo_lo = self.HEADER
+        self.off_halo_hi = self.HEADER + self.plane_bytes
+        self.off_y = [self.HEADER + 2 * self.plane_bytes + par * self.y_bytes for par in (0, 1)]
+        total = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _cabi.check(self.lib.hs2_peer_alloc(total, ctypes.byref(ptr), handle))
+        self.base = {rank: ptr.value}
+        self._own = ptr.value
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self._opened = []
+        for r in self.peers:
+            q = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                _cabi.check(self.lib.hs2_peer_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q)))
+            self.base[r] = q.value
+            self._opened.append(q.value)
+        dist.barrier(group=group)
+        self.step_no = 0
+
+    # virtual base address of the [2*P_glob][n_lines] interface array in rank r's mailbox
+    def y_virtual(self, r, parity):
+        return self.base[r] + self.off_y[parity] - (r - self.hops) * self.slab_bytes
+
+    def y_rows_of(self, r, parity, src):
+        """where slab ``src``'s rows live in rank r's mailbox"""
+        return self.y_virtual(r, parity) + src * self.slab_bytes
+
+    def status(self):
+        out = torch.zeros(1, dtype=torch.int32)
+        torch.cuda.synchronize()
+        _cabi.check(self.lib.hs2_copy_async(out.data_ptr(), self._own + self.OFF_STATUS, 4, None))
+        torch.cuda.synchronize()
+        return int(out[0])
+
+    def close(self):
+        for q in self._opened:
+            self.lib.hs2_peer_close(q)
+        self._opened = []
+        if self._own:
+            self.lib.hs2_peer_free(self._own)
+            self._own = 0
+
+
+def _u64_list(vals):
+    return (ctypes.c_uint64 * max(1, len(vals)))(*vals), len(vals)
+
+
 class DistPlan(object):
     """Slab plan + the communication of one rank."""
 
@@ -61,6 +144,10 @@ class DistPlan(object):
         self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "1" if self.world <= 2 else "2"))
         self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
         self._bufs = {}
+        self.use_p2p = os.environ.get("HS2_DIST_P2P", "1") != "0"
+        self.p2p_timeout = float(os.environ.get("HS2_DIST_TIMEOUT_S", "20"))
+        self._px = None
+        self.profile = None          # list: when set, _step_p2p appends 7 CUDA events per step
 
     # ------------------------------------------------------------- buffers
     def _buf(self, name, shape, like):
@@ -98,6 +185,89 @@ class DistPlan(object):
 
     def _prepare(self, T_in):
         self.plan.ensure_device(T_in.device)
+
+    # ----------------------------------------------- peer-memory transport
+    def _peer_exchange(self, T_in):
+        """The mailbox set-up is collective: the first step of every rank creates it."""
+        if self._px is None and self.use_p2p and T_in.is_cuda and self.world > 1:
+            try:
+                ny, nx = self.shape[1:]
+                self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device)
+            except NotImplementedError:
+                self.use_p2p = False
+        return self._px
+
+    def _step_p2p(self, px, T_in, T_out, work, src, keep):
+        lib = _cabi.lib()
+        st = self._stream(T_in)
+        px.step_no += 1
+        n = px.step_no
+        par = n & 1
+        me, lo, hi = self.rank, self.rank - 1, self.rank + 1
+        own = px.base[me]
+        sig, wait = [], []
+        h = self.shape[0]
+        ev = None
+        if self.profile is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            self.profile.append(ev)
+            ev[0].record()
+        # halo planes of T_in into the neighbours' mailboxes, then tell them
+        if lo >= 0:
+            _cabi.check(lib.hs2_copy_async(px.base[lo] + px.off_halo_hi, T_in.data_ptr(), px.plane_bytes, st))
+            sig.append(px.base[lo] + px.OFF_FLAG_H_HI)
+            wait.append(own + px.OFF_FLAG_H_LO)
+        if hi < self.world:
+            _cabi.check(lib.hs2_copy_async(px.base[hi] + px.off_halo_lo, T_in.data_ptr() + (h - 1) * px.plane_bytes,
+                                           px.plane_bytes, st))
+            sig.append(px.base[hi] + px.OFF_FLAG_H_LO)
+            wait.append(own + px.OFF_FLAG_H_HI)
+        arr, cnt = _u64_list(sig)
+        _cabi.check(lib.hs2_flag_signal(arr, cnt, n, st))
+        arr, cnt = _u64_list(wait)
+        _cabi.check(lib.hs2_flag_wait(arr, cnt, n, self.p2p_timeout, own + px.OFF_STATUS, st))
+        if ev: ev[1].record()
+        _cabi.check(lib.hs2_sweep_x(self.plan._handle, T_in.data_ptr(), work.data_ptr(),
+                                    ctypes.byref(src) if src is not None else None,
+                                    own + px.off_halo_lo if lo >= 0 else None,
+                                    own + px.off_halo_hi if hi < self.world else None, st))
+        if ev: ev[2].record()
+        _cabi.check(lib.hs2_sweep_y(self.plan._handle, work.data_ptr(), st))
+        if ev: ev[3].record()
+        # z: eliminate the local chunks; their interface values go to every slab in reach
+        arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
+        _cabi.check(lib.hs2_sweep_z_forward_push(self.plan._handle, work.data_ptr(), px.y_rows_of(me, par, me), cnt, arr, st))
+        if ev: ev[4].record()
+        arr, cnt = _u64_list([px.base[r] + 8 * me for r in px.peers])
+        _cabi.check(lib.hs2_flag_signal(arr, cnt, n, st))
+        arr, cnt = _u64_list([own + 8 * r for r in px.peers])
+        _cabi.check(lib.hs2_flag_wait(arr, cnt, n, self.p2p_timeout, own + px.OFF_STATUS, st))
+        if ev: ev[5].record()
+        _cabi.check(lib.hs2_sweep_z_backward(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
+                                             px.y_virtual(me, par), 0, self.shape[1] * self.shape[2], st))
+        if ev: ev[6].record()
+        return T_out
+
+    PHASES = ("halo_push_wait", "x", "y", "z_forward_push", "interface_wait", "z_backward")
+
+    def profile_ms(self):
+        """mean milliseconds per phase over the profiled steps (synchronises)"""
+        torch.cuda.synchronize()
+        if not self.profile:
+            return None
+        n = len(self.profile)
+        return {name: sum(e[i].elapsed_time(e[i + 1]) for e in self.profile) / n for i, name in enumerate(self.PHASES)}
+
+    def check(self):
+        """Raise if a peer-memory wait ever timed out (synchronises the device)."""
+        if self._px is not None and self._px.status() != 0:
+            raise RuntimeError("heatsim2_b200.dist: a peer did not deliver its data within %.0f s" % self.p2p_timeout)
+
+    def close(self):
+        if self._px is not None:
+            torch.cuda.synchronize()
+            self._px.close()
+            self._px = None
 
     # ------------------------------------------------------- communication
     def exchange_halos(self, T_in):
@@ -157,8 +327,14 @@ class DistPlan(object):
         src = keep = None
         if volumetric is not None and len(volumetric):
             src, keep = self.plan._source(t, dt, volumetric_elements, volumetric)
-        halo_lo, halo_hi = self.exchange_halos(T_in)
         work = self._buf("work", self.shape, T_in)
+        px = self._peer_exchange(T_in)
+        if px is not None:
+            self._step_p2p(px, T_in, T_out, work, src, keep)
+            if keep is not None and len(keep) > 1:
+                torch.cuda.current_stream(T_in.device).synchronize()
+            return T_out
+        halo_lo, halo_hi = self.exchange_halos(T_in)
         self._k_sweep_x(T_in, work, src, keep, halo_lo, halo_hi)
         self._k_sweep_y(work)
         # z-sweep, pipelined over ranges of lines: while the interface values of
@@ -196,8 +372,12 @@ class DistPlan(object):
             peers = self.world - 1
         else:
             peers = sum(1 for d in range(1, self.hops + 1) for r in (self.rank - d, self.rank + d) if 0 <= r < self.world)
-        return {"halo_send": halo, "interface_send": 2 * self.p_loc * ny * nx * 8 * peers,
-                "interface_mode": "all-gather" if 2 * self.hops >= self.world - 1 else "%d-hop neighbours" % self.hops}
+        if self._px is not None:
+            peers = len(self._px.peers)
+            mode = "peer-memory stores from the z_forward kernel to %d slab(s), flags in peer memory" % peers
+        else:
+            mode = "NCCL all-gather" if 2 * self.hops >= self.world - 1 else "NCCL send/recv, %d-hop neighbours" % self.hops
+        return {"halo_send": halo, "interface_send": 2 * self.p_loc * ny * nx * 8 * peers, "interface_mode": mode}
 
 
 def setup(z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric,

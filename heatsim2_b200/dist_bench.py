@@ -61,6 +61,17 @@ def run(args, shape, workload_name):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
+    dplan.check()
+    # per-phase device times of a few extra steps (peer-memory transport only; not part of the timed region)
+    phase_ms = None
+    if dplan._px is not None:
+        dplan.profile = []
+        for _ in range(5):
+            hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
+            Ta, Tb = Tb, Ta
+            it += 1
+        phase_ms = dplan.profile_ms()
+        dplan.profile = None
     # e2e: every step each rank uploads its slab from pinned host memory and reads the result back
     H_in = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
     H_out = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
@@ -90,7 +101,7 @@ def run(args, shape, workload_name):
         if os.path.exists(pk):
             peak, peak_src = json.load(open(pk))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy), per GPU"
         value = n_global / (ms_step * 1e-3)
-        bytes_cell = 72          # distributed z-sweep re-reads/re-writes the increment once: 16 + 16 + 40
+        bytes_cell = 64          # distributed z-sweep reads the increment twice: 16 + 16 + 8 + 24
         comm = dplan.comm_bytes_per_step()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -105,12 +116,15 @@ def run(args, shape, workload_name):
                              "note": "algorithmic 56 B/cell-update; the slab z-sweep actually moves %d B/cell" % bytes_cell},
                 "comm": {"halo_bytes_per_rank_per_step": comm["halo_send"],
                          "interface_bytes_sent_per_rank_per_step": comm["interface_send"],
-                         "interface_exchange": comm["interface_mode"], "pipeline_ranges": len(dplan._line_ranges(shape[1] * shape[2])),
-                         "backend": "NCCL %s over NVLink" % ".".join(str(v) for v in torch.cuda.nccl.version())},
+                         "interface_exchange": comm["interface_mode"], "rank0_phase_ms": phase_ms,
+                         "backend": ("CUDA IPC peer memory over NVLink (NCCL only for set-up)" if dplan._px is not None else
+                                     "NCCL %s over NVLink" % ".".join(str(v) for v in torch.cuda.nccl.version()))},
                 "cpu_baseline": None,
                 "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_global * 8,
                         "d2h_bytes_per_step": n_global * 8, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "api": "per rank: pinned host slab -> device, heatsim2_b200.run_adi_steps (dist plan), device -> pinned host"},
-                "gpu_launches": args.steps * 4 * world}
+                "gpu_launches": args.steps * (8 if dplan._px is not None else 4) * world}
         print(json.dumps(line))
+    dplan.check()
+    dplan.close()
     dist.destroy_process_group()

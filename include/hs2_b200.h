@@ -170,6 +170,32 @@ int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out,
                          double *d_work, const double *d_Yall,
                          int64_t line0, int64_t n_lines, void *stream);
 
+/* NVLink peer-memory variant of the exchange (one process per GPU, all on one
+ * node).  hs2_peer_alloc returns zero-initialised device memory and a 64-byte
+ * CUDA IPC handle; another process maps it with hs2_peer_open.  The z-interface
+ * values are then written by the producing kernel itself:
+ * hs2_sweep_z_forward_push = hs2_sweep_z_forward over all lines that also
+ * stores this slab's 2*nz/chunk rows at peer_Y[i] (device addresses inside the
+ * peers' mapped buffers, row pitch ny*nx doubles), i < n_peers <=
+ * HS2_MAX_Z_PEERS.  Ordering between GPUs is by 64-bit flags in peer memory:
+ * hs2_flag_signal stores `value` (release, system scope) to every listed flag
+ * after all earlier work of the stream; hs2_flag_wait holds the stream until
+ * every listed (local) flag is >= value, or sets *d_status = 1 after
+ * timeout_s seconds instead of hanging.  Flag lists are host arrays of device
+ * addresses, at most 16 entries.  hs2_copy_async = cudaMemcpyAsync between
+ * any two mapped device addresses (halo planes over NVLink).                */
+#define HS2_MAX_Z_PEERS 6
+int hs2_peer_alloc(int64_t bytes, void **d_ptr, void *handle64);
+int hs2_peer_open(const void *handle64, void **d_ptr);
+int hs2_peer_close(void *d_ptr);
+int hs2_peer_free(void *d_ptr);
+int hs2_sweep_z_forward_push(hs2_plan *plan, double *d_work, double *d_Y,
+                             int n_peers, const uint64_t *peer_Y, void *stream);
+int hs2_flag_signal(const uint64_t *flag_ptrs, int n, uint64_t value, void *stream);
+int hs2_flag_wait(const uint64_t *flag_ptrs, int n, uint64_t value,
+                  double timeout_s, int *d_status, void *stream);
+int hs2_copy_async(void *d_dst, const void *d_src, int64_t bytes, void *stream);
+
 /* Drop-ins for heatsim2/tridiag.pyx on device arrays.
  * hs2_tridiag_lu    = tridiaglu   (:9-43):  A[n][3] -> L[n][3], U[n][3]
  * hs2_tridiag_solve = tridiagsolve(:46-69): x = U^-1 L^-1 b, one chain of n

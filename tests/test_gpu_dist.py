@@ -25,11 +25,13 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, kwargs, nsteps, q):
+def _worker(rank, world, port, name, kwargs, nsteps, q, p2p):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["HS2_DIST_P2P"] = "1" if p2p else "0"
+    os.environ["HS2_DIST_TIMEOUT_S"] = "10"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -43,38 +45,53 @@ def _worker(rank, world, port, name, kwargs, nsteps, q):
         for it in range(nsteps):
             T = hs.run_adi_steps(P, S, prob["t0"] + it * prob["dt"], prob["dt"], T, ve, prob["volumetric"])
         torch.cuda.synchronize()
+        assert (P.plan._px is not None) == bool(p2p)
+        P.plan.check()
         q.put((rank, T.cpu().numpy()))
+        P.plan.close()
+    except Exception as exc:          # report instead of leaving the parent waiting
+        import traceback
+        q.put((rank, "ERROR in rank %d: %s\n%s" % (rank, exc, traceback.format_exc())))
+        raise
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, name, kwargs, nsteps):
+def _run(world, name, kwargs, nsteps, p2p=True):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
-    parts = [q.get(timeout=600) for _ in range(world)]
+    try:
+        parts = [q.get(timeout=240) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    for part in parts:
+        assert not isinstance(part[1], str), part[1]
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
     parts.sort(key=lambda t: t[0])
     return np.concatenate([p[1] for p in parts], axis=0)
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer-memory", "nccl"])
 @pytest.mark.parametrize("name,kwargs,nsteps", [
     ("steelonfoam", dict(nz=64, ny=40, nx=48), 6),
     ("uniform_slab", dict(shape=(128, 48, 64)), 4),
     ("composite", dict(nz=64, ny=32, nx=32, ply=8), 4),
 ])
-def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps):
+def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
     import adi_oracle
     import heatsim2_b200 as hs
     world = min(_ngpu(), 4) if name == "uniform_slab" else 2
-    got = _run(world, name, kwargs, nsteps)
+    got = _run(world, name, kwargs, nsteps, p2p)
     prob = problems.ALL[name](hs, **kwargs)
     one = util.run_b200(hs, prob, nsteps=nsteps)
     assert util.relerr(got, one) <= 1e-13

@@ -116,3 +116,23 @@ def test_device_resident_loop_with_observation(hs):
     assert util.relerr(Tn, z["T_100"]) <= 1e-10
     want_surface = hs.surface_temperature.insulating_z_min_surface_temperature(Tn, prob["dz"])
     assert util.relerr(rec["surface"][-1], want_surface) <= 1e-14
+
+
+@pytest.mark.parametrize("name,kwargs,world,nsteps", [
+    ("steelonfoam", dict(nz=64, ny=40, nx=48), 2, 6),
+    ("uniform_slab", dict(shape=(128, 48, 64)), 4, 4),
+    ("uniform_slab", dict(shape=(64, 40, 50)), 8, 3),
+    ("composite", dict(nz=64, ny=32, nx=32, ply=8), 2, 4),
+    ("steelonwater", dict(nz=64, ny=40, nx=48), 2, 4),
+])
+def test_slab_kernels_on_one_gpu(hs, name, kwargs, world, nsteps):
+    """The kernels of the multi-GPU z-slab path, slabs run one after the other
+    on this GPU (tests/slab_seq.py): same field as the single plan (1e-13) and
+    as the oracle (1e-12)."""
+    import adi_oracle
+    import slab_seq
+    prob = problems.ALL[name](hs, **kwargs)
+    got = slab_seq.run(hs, prob, world, nsteps)
+    one = util.run_b200(hs, prob, nsteps=nsteps)
+    assert util.relerr(got, one) <= 1e-13
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=nsteps)) <= 1e-12
