@@ -56,6 +56,8 @@ PROTOTYPES = {
     "hs2_plan_launches_per_step": (ctypes.c_int, [c_void_p]),
     "hs2_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
+    "hs2_sweep_x_part": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, ctypes.c_int,
+                                        c_void_p]),
     "hs2_sweep_y": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_z": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_z_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p]),

@@ -67,10 +67,23 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
   if (hs2_tile_xf_supported(plan))
-    return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
+    return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream);
   if (hs2_tile_x_supported(plan))
     return hs2_tile_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
   return hs2_v1_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
+}
+
+int hs2_sweep_x_part(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src,
+                     const double *d_halo_lo, const double *d_halo_hi, int part, void *stream) {
+  HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x_part: NULL argument");
+  HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x_part: d_work must not alias d_T_in");
+  HS2_REQUIRE(part == HS2_X_INTERIOR || part == HS2_X_BOUNDARY, "hs2_sweep_x_part: part must be HS2_X_INTERIOR or HS2_X_BOUNDARY");
+  if (!hs2_tile_xf_supported(plan) || plan->d.nz < 3) {
+    // kernels without plane ranges: everything happens in the boundary call
+    if (part == HS2_X_INTERIOR) return HS2_OK;
+    return hs2_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, stream);
+  }
+  return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, part, (cudaStream_t)stream);
 }
 
 int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream) {

@@ -70,4 +70,4 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
 // kernels_xf.cu - x sweep with the explicit x-term folded into the solve (default)
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
-                      const double *halo_hi, cudaStream_t st);
+                      const double *halo_hi, int part, cudaStream_t st);

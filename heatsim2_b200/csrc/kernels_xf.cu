@@ -40,10 +40,13 @@
 
 namespace {
 
-constexpr int R = HS2_XR;  // lines per tile
+// pad words per chunk in the shared-memory tile: 2 for 8-line tiles; 4-line
+// tiles put two chunks into a quarter warp, which needs the chunk stride to be
+// 4 (mod 8) 16-byte units
+__host__ __device__ constexpr int xf_pad(int R, int M) { return R >= 8 ? 2 : (M == 8 ? 0 : 8); }
 
-__host__ __device__ inline int xf_row_pitch(int P, int M) {
-  int s = P * (M + 2);
+__host__ __device__ inline int xf_row_pitch(int P, int M, int pad) {
+  int s = P * (M + pad);
   while ((s & 3) != 2) s += 2;
   return s;
 }
@@ -137,16 +140,17 @@ __device__ __forceinline__ void xf_backward_short(double (&v)[M], const XTab<M> 
   }
 }
 
-template <int M, typename CID>
+template <int M, int R, typename CID>
 __global__ void __launch_bounds__(256, 2)
 sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const CID *__restrict__ cid,
                 const double *__restrict__ coef_g, int n_classes, int coef_in_smem, const uint8_t *__restrict__ vol,
                 SrcTab st, const double *__restrict__ dense, const double *__restrict__ halo_lo,
                 const double *__restrict__ halo_hi, const uint32_t *__restrict__ line_id,
                 const double2 *__restrict__ xtab, const double *__restrict__ GE, int nz, int ny, int nx, int P, int band,
-                int tiles_y, int n_tiles, int pf) {
+                int tiles_y, int n_tiles, int pf, int part) {
   extern __shared__ __align__(16) double sm[];
-  const int Sr = xf_row_pitch(P, M);
+  constexpr int PAD = xf_pad(R, M);
+  const int Sr = xf_row_pitch(P, M, PAD);
   double *buf = sm;            // [R][Sr]
   double *Y = buf + R * Sr;    // [2P][R]
   double *Es = Y + 2 * P * R;  // [P][R]
@@ -167,9 +171,13 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
   const int c0 = pc * M;
   const int rows = min(M, nx - c0);
   const bool full = rows == M;
-  double *mine = buf + r2 * Sr + pc * (M + 2);
+  double *mine = buf + r2 * Sr + pc * (M + PAD);
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // part 0: every plane; 1: interior planes 1..nz-2 (need no halo); 2: the two
+  // boundary planes 0 and nz-1 (a slab's first/last plane read the neighbours' halos)
+  const int n_work = part == 0 ? n_tiles : (part == 1 ? n_tiles - 2 * tiles_y : 2 * tiles_y);
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int tile = part == 0 ? work : (part == 1 ? work + tiles_y : (work < tiles_y ? work : n_tiles - 2 * tiles_y + work));
     const int k = tile / tiles_y;
     const int j0 = (tile % tiles_y) * R;
     const int64_t kbase = (int64_t)k * plane;
@@ -180,7 +188,7 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
       // the only rows of a tile nobody has touched yet are its z+ neighbours:
       // ask L2 for those of this block's NEXT tile now (128-byte lines)
       const int tn = tile + gridDim.x;
-      if (tn < n_tiles) {
+      if (part == 0 && tn < n_tiles) {
         const int kn = tn / tiles_y, jn = (tn % tiles_y) * R;
         if (kn + 1 < nz) {
           const double *nxt = T + (int64_t)(kn + 1) * plane + (int64_t)jn * nx;
@@ -197,7 +205,8 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
     const double *zhi = k < nz - 1 ? T + kbase + plane : (halo_hi ? halo_hi : T + kbase);
     const double *Tk = T + kbase;
     const CID *cidk = cid + kbase;
-    constexpr int RH = R / 2;  // rows per register batch
+    constexpr int NB = R >= 8 ? 2 : 1;  // register batches per column pair
+    constexpr int RH = R / NB;          // rows per batch
     // in-plane offsets (32-bit: ny*nx < 2^31) of the window rows j0-1 .. j0+R, clamped to the plane
     int ro[R + 2];
 #pragma unroll
@@ -207,13 +216,13 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
       ro[q] = j * nx;
     }
     for (int i = 2 * tid; i < nx; i += 2 * nthreads) {
-      double *bcol = buf + i + 2 * (i / M);
+      double *bcol = buf + i + PAD * (i / M);
       int last_id = -1;
       double2 cy = make_double2(0, 0), cz = cy;
       double csrc = 0.0;
       double2 tc[R + 2];  // y-window: tc[q] = row j0 + q - 1
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NB; ++h) {
         const int rb = h * RH;
         double2 zm[RH], zp[RH];
         int id[RH];
@@ -334,7 +343,7 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
     // ------------------------------------------------ phase 3: d1 = w - 2T, coalesced store
     double *Wk = Wout + kbase + (int64_t)j0 * nx;
     for (int i = 2 * tid; i < nx; i += 2 * nthreads) {
-      const double *bcol = buf + i + 2 * (i / M);
+      const double *bcol = buf + i + PAD * (i / M);
       double2 t0[R], w[R];
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -352,19 +361,19 @@ sweep_xf_kernel(const double *__restrict__ T, double *__restrict__ Wout, const C
   }
 }
 
-template <int M, typename CID>
+template <int M, int R, typename CID>
 int launch_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const SrcTab &tabsrc, const double *halo_lo,
-              const double *halo_hi, cudaStream_t st) {
+              const double *halo_hi, int part, cudaStream_t st) {
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
   const int P = ax.n_chunks;
   const int threads = R * P;
-  const int Sr = xf_row_pitch(P, M);
+  const int Sr = xf_row_pitch(P, M, xf_pad(R, M));
   const int coef_in_smem = d.n_classes <= 256 ? 1 : 0;
   const size_t smem = ((size_t)R * Sr + 3 * (size_t)P * R + (coef_in_smem ? (size_t)d.n_classes * HS2_COEF_STRIDE : 0)) *
                       sizeof(double);
   HS2_REQUIRE(smem <= (size_t)p->max_smem_optin, "x sweep: tile needs %zu B of shared memory", smem);
-  auto kern = sweep_xf_kernel<M, CID>;
+  auto kern = sweep_xf_kernel<M, R, CID>;
   if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int resident = 65536 / (threads * 128) > 0 ? 65536 / (threads * 128) : 1;
   while (resident > 1 && resident * (smem + 1024) > 227 * 1024) --resident;
@@ -379,26 +388,39 @@ int launch_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, co
   const int tiles_y = (int)((d.ny + R - 1) / R);
   const int64_t n_tiles = d.nz * tiles_y;
   HS2_REQUIRE(n_tiles < ((int64_t)1 << 31), "x sweep: too many tiles");
+  const int64_t n_work = part == 0 ? n_tiles : (part == 1 ? n_tiles - 2 * tiles_y : 2 * (int64_t)tiles_y);
+  if (n_work <= 0) return HS2_OK;
   int64_t blocks = (int64_t)p->sm_count * resident;
-  if (blocks > n_tiles) blocks = n_tiles;
+  if (blocks > n_work) blocks = n_work;
   const uint8_t *vol = (src && tabsrc.n) ? src->d_vol_elements : nullptr;
   const double *dense = src ? src->d_dense : nullptr;
   static const int pf = getenv("HS2_X_PREFETCH") ? atoi(getenv("HS2_X_PREFETCH")) : 0;   // measured on B200: the prefetch costs 0.05 ms
   kern<<<(unsigned)blocks, threads, smem, st>>>(T, W, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes, coef_in_smem,
                                                  vol, tabsrc, dense, halo_lo, halo_hi, ax.d_line_id,
                                                  reinterpret_cast<const double2 *>(ax.d_tab_il), ax.d_GE, (int)d.nz,
-                                                 (int)d.ny, (int)d.nx, P, ax.band, tiles_y, (int)n_tiles, pf);
+                                                 (int)d.ny, (int)d.nx, P, ax.band, tiles_y, (int)n_tiles, pf, part);
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
 }
 
 template <typename CID>
 int dispatch_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const SrcTab &tabsrc,
-                const double *halo_lo, const double *halo_hi, cudaStream_t st) {
+                const double *halo_lo, const double *halo_hi, int part, cudaStream_t st) {
+  // 8-line tiles.  4-line tiles (HS2_X_R=4: twice the blocks per SM for lines of
+  // more than 16 chunks) measured slower on B200 at nx = 512 and nx = 1024.
+  static const int r_env = getenv("HS2_X_R") ? atoi(getenv("HS2_X_R")) : 0;
+  const bool small = r_env == 4;
+  if (small) {
+    switch (p->d.axis[0].chunk) {
+      case 8: return launch_xf<8, 4, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+      case 16: return launch_xf<16, 4, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+      case 32: return launch_xf<32, 4, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+    }
+  }
   switch (p->d.axis[0].chunk) {
-    case 8: return launch_xf<8, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
-    case 16: return launch_xf<16, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
-    case 32: return launch_xf<32, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+    case 8: return launch_xf<8, 8, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+    case 16: return launch_xf<16, 8, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+    case 32: return launch_xf<32, 8, CID>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
   }
   hs2_set_error("x sweep: unsupported chunk size %d", p->d.axis[0].chunk);
   return HS2_E_INVALID;
@@ -413,12 +435,13 @@ bool hs2_tile_xf_supported(const hs2_plan *p) {
 }
 
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
-                      const double *halo_hi, cudaStream_t st) {
+                      const double *halo_hi, int part, cudaStream_t st) {
+  HS2_REQUIRE(part == 0 || (part >= 1 && part <= 2 && p->d.nz >= 2), "x sweep: bad part %d", part);
   SrcTab tabsrc;
   int rc = hs2_make_src_tab(src, &tabsrc);
   if (rc) return rc;
-  if (p->d.class_id_bytes == 1) return dispatch_xf<uint8_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
-  return dispatch_xf<uint16_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, st);
+  if (p->d.class_id_bytes == 1) return dispatch_xf<uint8_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
+  return dispatch_xf<uint16_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
 }
 
 #ifdef HS2_PHASE_TIMING

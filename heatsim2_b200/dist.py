@@ -224,13 +224,15 @@ class DistPlan(object):
             wait.append(own + px.OFF_FLAG_H_HI)
         arr, cnt = _u64_list(sig)
         _cabi.check(lib.hs2_flag_signal(arr, cnt, n, st))
+        # interior planes need no halo: solve them while the neighbours' planes travel
+        srcp = ctypes.byref(src) if src is not None else None
+        h_lo = own + px.off_halo_lo if lo >= 0 else None
+        h_hi = own + px.off_halo_hi if hi < self.world else None
+        _cabi.check(lib.hs2_sweep_x_part(self.plan._handle, T_in.data_ptr(), work.data_ptr(), srcp, h_lo, h_hi, 1, st))
+        if ev: ev[1].record()
         arr, cnt = _u64_list(wait)
         _cabi.check(lib.hs2_flag_wait(arr, cnt, n, self.p2p_timeout, own + px.OFF_STATUS, st))
-        if ev: ev[1].record()
-        _cabi.check(lib.hs2_sweep_x(self.plan._handle, T_in.data_ptr(), work.data_ptr(),
-                                    ctypes.byref(src) if src is not None else None,
-                                    own + px.off_halo_lo if lo >= 0 else None,
-                                    own + px.off_halo_hi if hi < self.world else None, st))
+        _cabi.check(lib.hs2_sweep_x_part(self.plan._handle, T_in.data_ptr(), work.data_ptr(), srcp, h_lo, h_hi, 2, st))
         if ev: ev[2].record()
         _cabi.check(lib.hs2_sweep_y(self.plan._handle, work.data_ptr(), st))
         if ev: ev[3].record()
@@ -248,7 +250,7 @@ class DistPlan(object):
         if ev: ev[6].record()
         return T_out
 
-    PHASES = ("halo_push_wait", "x", "y", "z_forward_push", "interface_wait", "z_backward")
+    PHASES = ("halo_push+x_interior", "halo_wait+x_boundary", "y", "z_forward_push", "interface_wait", "z_backward")
 
     def profile_ms(self):
         """mean milliseconds per phase over the profiled steps (synchronises)"""

@@ -150,6 +150,15 @@ int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out,
 int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work,
                 const hs2_source *src, const double *d_halo_lo,
                 const double *d_halo_hi, void *stream);
+/* hs2_sweep_x in two launches, so that a slab's halo exchange can travel while
+ * the planes that do not need it are being solved: HS2_X_INTERIOR = planes
+ * 1..nz-2 (the halo pointers are not read), HS2_X_BOUNDARY = planes 0 and nz-1.
+ * Both calls together equal one hs2_sweep_x.                                  */
+#define HS2_X_INTERIOR 1
+#define HS2_X_BOUNDARY 2
+int hs2_sweep_x_part(hs2_plan *plan, const double *d_T_in, double *d_work,
+                     const hs2_source *src, const double *d_halo_lo,
+                     const double *d_halo_hi, int part, void *stream);
 int hs2_sweep_y(hs2_plan *plan, double *d_work, void *stream);
 int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out,
                 double *d_work, void *stream);

@@ -43,10 +43,12 @@ def run(hs, prob, world, nsteps):
                 src, keep = pl._source(t, dt, ve[r * h:(r + 1) * h], volumetric)
             lo = T[r - 1][-1].clone() if r > 0 else None
             hi = T[r + 1][0].clone() if r < world - 1 else None
-            _cabi.check(lib.hs2_sweep_x(pl._handle, T[r].data_ptr(), work[r].data_ptr(),
-                                        ctypes.byref(src) if src is not None else None,
-                                        lo.data_ptr() if lo is not None else None,
-                                        hi.data_ptr() if hi is not None else None, st))
+            # the two-launch form the peer-memory transport uses: interior planes, then the boundary planes
+            for part in (1, 2):
+                _cabi.check(lib.hs2_sweep_x_part(pl._handle, T[r].data_ptr(), work[r].data_ptr(),
+                                                 ctypes.byref(src) if src is not None else None,
+                                                 lo.data_ptr() if lo is not None else None,
+                                                 hi.data_ptr() if hi is not None else None, part, st))
             _cabi.check(lib.hs2_sweep_y(pl._handle, work[r].data_ptr(), st))
             own = Yall[r * 2 * p_loc:(r + 1) * 2 * p_loc]
             _cabi.check(lib.hs2_sweep_z_forward(pl._handle, work[r].data_ptr(), own.data_ptr(), 0, n_lines, st))
