@@ -59,7 +59,7 @@ int hs2_plan_destroy(hs2_plan *plan) {
 
 int hs2_plan_launches_per_step(const hs2_plan *plan) {
   if (!plan) return 0;
-  return (hs2_tile_x_supported(plan) ? 1 : 2) + 2;
+  return (hs2_tile_xf_supported(plan) ? 1 : 2) + 2;
 }
 
 int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src, const double *d_halo_lo,
@@ -68,8 +68,6 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
   if (hs2_tile_xf_supported(plan))
     return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream);
-  if (hs2_tile_x_supported(plan))
-    return hs2_tile_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
   return hs2_v1_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
 }
 

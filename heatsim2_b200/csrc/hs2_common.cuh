@@ -58,13 +58,10 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
 int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
 
-// kernels_strided.cu / kernels_x.cu - register/shared-memory tile kernels
+// kernels_strided.cu - register/shared-memory tile kernels of the strided axes
 bool hs2_tile_supported(const hs2_plan *p, int axis);
 int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
-bool hs2_tile_x_supported(const hs2_plan *p);
-int hs2_tile_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
-                     const double *halo_hi, cudaStream_t st);
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
               int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st);
 // kernels_xf.cu - x sweep with the explicit x-term folded into the solve (default)

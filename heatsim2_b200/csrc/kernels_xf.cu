@@ -429,9 +429,12 @@ int dispatch_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, 
 }  // namespace
 
 bool hs2_tile_xf_supported(const hs2_plan *p) {
-  static const bool off = getenv("HS2_X_KERNEL") != nullptr && getenv("HS2_X_KERNEL")[0] == 'o';
-  if (off || !hs2_tile_x_supported(p)) return false;
-  return p->d.axis[0].d_tab_il != nullptr;
+  if (!hs2_tile_supported(p, 0)) return false;
+  const hs2_plan_desc &d = p->d;
+  if (d.nx >= ((int64_t)1 << 30) || d.ny >= ((int64_t)1 << 30) || d.nz >= ((int64_t)1 << 30)) return false;
+  if (d.ny * d.nx >= ((int64_t)1 << 31)) return false;   // 32-bit in-plane offsets
+  if (d.nx & 1) return false;                            // column pairs need 16-byte aligned rows
+  return d.axis[0].n_chunks * 8 <= 256 && d.axis[0].d_tab_il != nullptr;
 }
 
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,

@@ -29,7 +29,9 @@ __global__ void flag_signal_kernel(FlagList fl, unsigned long long value) {
 // word is set and the kernel returns, so a lost peer can never hang the GPU.
 __global__ void flag_wait_kernel(FlagList fl, unsigned long long value, long long max_cycles, int *status) {
   const int i = threadIdx.x;
-  if (i < fl.n) {
+  // once a wait has timed out the run is lost: later waits return at once, so
+  // the process reaches its status check quickly instead of timing out per step
+  if (i < fl.n && *reinterpret_cast<volatile int *>(status) == 0) {
     const long long t0 = clock64();
     for (;;) {
       unsigned long long v;

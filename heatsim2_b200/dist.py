@@ -78,21 +78,34 @@ class PeerExchange(object):
         self.off_halo_hi = self.HEADER + self.plane_bytes
         self.off_y = [self.HEADER + 2 * self.plane_bytes + par * self.y_bytes for par in (0, 1)]
         total = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
+        # every step below is collective: a failure on any rank (no IPC support, no
+        # peer access) makes ALL ranks give up, so that they fall back to NCCL together
         ptr = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
+        self._own, self._opened, self.base = 0, [], {}
         with torch.cuda.device(device):
-            _cabi.check(self.lib.hs2_peer_alloc(total, ctypes.byref(ptr), handle))
-        self.base = {rank: ptr.value}
-        self._own = ptr.value
-        handles = [None] * world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self._opened = []
-        for r in self.peers:
-            q = ctypes.c_void_p()
-            with torch.cuda.device(device):
-                _cabi.check(self.lib.hs2_peer_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q)))
-            self.base[r] = q.value
-            self._opened.append(q.value)
+            ok = self.lib.hs2_peer_alloc(total, ctypes.byref(ptr), handle) == 0
+        if ok:
+            self._own = ptr.value
+            self.base[rank] = ptr.value
+        infos = [None] * world
+        dist.all_gather_object(infos, (ok, handle.raw), group=group)
+        ok = all(i[0] for i in infos)
+        if ok:
+            for r in self.peers:
+                q = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    if self.lib.hs2_peer_open(ctypes.create_string_buffer(infos[r][1], 64), ctypes.byref(q)) != 0:
+                        ok = False
+                        break
+                self.base[r] = q.value
+                self._opened.append(q.value)
+        oks = [None] * world
+        dist.all_gather_object(oks, ok, group=group)
+        if not all(oks):
+            why = self.lib.hs2_last_error().decode("utf-8", "replace")
+            self.close()
+            raise NotImplementedError("peer memory unavailable on at least one rank (%s)" % why)
         dist.barrier(group=group)
         self.step_no = 0
 
@@ -193,8 +206,9 @@ class DistPlan(object):
             try:
                 ny, nx = self.shape[1:]
                 self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device)
-            except NotImplementedError:
+            except NotImplementedError as exc:
                 self.use_p2p = False
+                self.p2p_unavailable = str(exc)
         return self._px
 
     def _step_p2p(self, px, T_in, T_out, work, src, keep):

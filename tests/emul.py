@@ -64,7 +64,7 @@ def chunk_backward(u, tab, M, E, alpha, row0=0):
 
 
 def solve_axis(plan, W, axis):
-    """single-device chunked solve of all lines of `axis` (kernels_strided.cu / kernels_x.cu phase 2)"""
+    """single-device chunked solve of all lines of `axis` (kernels_strided.cu / kernels_xf.cu phase 2)"""
     M, P = plan.chunk[axis]
     tab_u, GE_u = plan.chunk_tabs[axis]
     lid = plan.line_id[axis].cpu().numpy()
@@ -78,7 +78,7 @@ def solve_axis(plan, W, axis):
 
 
 def rhs(plan, T, src_dense, halo_lo, halo_hi):
-    """stage-0 right hand side, kernels_x.cu phase 1"""
+    """stage-0 right hand side (unfolded form; kernels_xf.cu folds the x-term into the solve)"""
     cid = plan.class_id.cpu().numpy().astype(np.int64) & 0xFFFF
     c = plan.scaled_coef[cid]
     Tp = np.pad(T, 1, mode="edge")
