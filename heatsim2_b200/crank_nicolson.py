@@ -100,16 +100,18 @@ def _as_u8(name, arr, shape):
     return a
 
 
-def _cell_keys(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device):
+def _cell_keys(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device, extra=None, extra_radix=1):
     """int64 equation key of every cell, computed in z-slabs to bound memory.
 
     Key digits (mixed radix), mirroring the reference's ``key_params`` (:296,
     :340-347): own material; effective material of the x+,y+,z+,x-,y-,z-
     neighbour (own material when the neighbour is outside the grid or
     TEMPERATURE_FIXED, :298-338); boundary class of the z-,z+,y-,y+,x-,x+
-    face.  TEMPERATURE_FIXED cells all get key -1."""
+    face.  ``extra`` (int64 tensor [nz,ny,nx] of values < ``extra_radix``) adds a
+    last digit - the geometry class of curved-surface mode.  TEMPERATURE_FIXED
+    cells all get key -1."""
     nz, ny, nx = material_elements.shape
-    radices = [n_mat] * 7 + [n_bnd] * 6
+    radices = [n_mat] * 7 + [n_bnd] * 6 + [int(extra_radix)]
     total = 1
     for r in radices:
         total *= r
@@ -158,14 +160,17 @@ def _cell_keys(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device):
         xf = torch.from_numpy(bx[k0:k1]).to(device).long()
         for f in (zf[:-1], zf[1:], yf[:, :-1], yf[:, 1:], xf[:, :, :-1], xf[:, :, 1:]):
             key = key * n_bnd + f
+        key = key * int(extra_radix)
+        if extra is not None:
+            key = key + extra[k0:k1].to(device)
         keys[k0:k1] = torch.where(fixed[m], torch.full_like(key, -1), key)
     return keys, radices, total
 
 
-def _classify(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device):
+def _classify(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device, extra=None, extra_radix=1):
     """Per-cell equation key -> dense class ids.  Returns (class_id int32
     tensor [nz,ny,nx], keys numpy int64 [n_classes] ascending, decode)."""
-    key, radices, total = _cell_keys(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device)
+    key, radices, total = _cell_keys(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device, extra, extra_radix)
     flat = key.reshape(-1)
     if total <= (1 << 26):
         # small key space: presence table + prefix sum, no sort
@@ -190,7 +195,7 @@ def _classify(material_elements, bz, by, bx, fixed_lut, n_mat, n_bnd, device):
             vals.append(int(k % r))
             k //= r
         vals.reverse()
-        return vals[0], vals[1:7], vals[7:13]
+        return vals[0], vals[1:7], vals[7:13], vals[13]
 
     return class_id, keys, decode
 
@@ -217,8 +222,7 @@ def compile_problem(z0, y0, x0,
     Shared by :func:`setup` (one GPU) and ``dist.setup`` (z-slabs)."""
     from . import TEMPERATURE_COMPUTE, TEMPERATURE_FIXED
     nz, ny, nx = int(nz), int(ny), int(nx)
-    if top_surface_y_curvatures is not None or top_surface_x_curvatures is not None:
-        raise NotImplementedError("curved-surface mode (top_surface_*_curvatures) is not implemented yet")
+    curved = top_surface_y_curvatures is not None or top_surface_x_curvatures is not None
     material_elements = _as_u8("material_elements", material_elements, (nz, ny, nx))
     bz = _as_u8("boundary_z_elements", boundary_z_elements, (nz + 1, ny, nx))
     by = _as_u8("boundary_y_elements", boundary_y_elements, (nz, ny + 1, nx))
@@ -235,7 +239,35 @@ def compile_problem(z0, y0, x0,
     work_dev = torch.device("cpu")
     if torch.cuda.is_available():
         work_dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    class_id, keys, decode = _classify(material_elements, bz, by, bx, fixed_lut, len(materials), len(boundaries), work_dev)
+
+    # Curved-surface mode (reference :388-458): the cell geometry depends on the
+    # two curvatures at (j, i) and on the depth index k, and so does the equation
+    # (the reference's key_params gain (curv_y, curv_x, k)).  Cells sharing a
+    # curvature pair and a depth share a class; the class tables cover up to
+    # 65536 classes, i.e. curvature that is constant or piecewise constant over
+    # (j, i).  Anything finer needs per-cell coefficients (not implemented).
+    extra, extra_radix, curv_pairs = None, 1, None
+    if curved:
+        cy = np.zeros((ny, nx)) if top_surface_y_curvatures is None else np.asarray(top_surface_y_curvatures, dtype=np.float64)
+        cx = np.zeros((ny, nx)) if top_surface_x_curvatures is None else np.asarray(top_surface_x_curvatures, dtype=np.float64)
+        if cy.shape != (ny, nx) or cx.shape != (ny, nx):
+            raise ValueError("top_surface_*_curvatures must have shape (ny, nx) = %r" % ((ny, nx),))
+        curv_pairs, curv_id = np.unique(np.stack([cy.reshape(-1), cx.reshape(-1)], axis=1), axis=0, return_inverse=True)
+        curv_id = curv_id.reshape(ny, nx)
+        if len(curv_pairs) * nz > 65536:
+            raise NotImplementedError(
+                "curved-surface mode with %d distinct curvature pairs x %d layers needs per-cell coefficients; "
+                "the class tables hold 65536 equation classes" % (len(curv_pairs), nz))
+        extra_radix = len(curv_pairs) * nz
+        extra = torch.from_numpy(curv_id[None, :, :] * nz + np.arange(nz)[:, None, None]).to(torch.int64)
+        kk = np.arange(nz, dtype=np.float64)[:, None, None]
+        dy_mean = 0.5 * ((1.0 + kk * cy[None] * dz) * dy + (1.0 + (kk + 1) * cy[None] * dz) * dy)
+        dx_mean = 0.5 * ((1.0 + kk * cx[None] * dz) * dx + (1.0 + (kk + 1) * cx[None] * dz) * dx)
+        # like the reference, volume_array stays 0 in TEMPERATURE_FIXED cells (:473-486)
+        volume_array = np.where(fixed_lut[material_elements], 0.0, np.abs(dx_mean * dy_mean * dz))
+    class_id, keys, decode = _classify(material_elements, bz, by, bx, fixed_lut, len(materials), len(boundaries), work_dev,
+                                       extra, extra_radix)
+    curved_boundaries = {}
 
     T555p = _operand("T555p")
     T555m = _operand("T555m")
@@ -246,16 +278,40 @@ def compile_problem(z0, y0, x0,
         if key < 0:
             value_key = (TEMPERATURE_FIXED,)
         else:
-            mat, nbrs, bnd = decode(int(key))
+            mat, nbrs, bnd, geom = decode(int(key))
             (_, matl_k, matl_rho, matl_c) = materials[mat]
             k_params = (matl_k,) + tuple(materials[nb][1] for nb in nbrs)
             k_hash = tuple(tuple(np.ravel(kp)) if isinstance(kp, np.ndarray) else kp for kp in k_params)
             value_key = (TEMPERATURE_COMPUTE, tuple(bnd), k_hash, matl_rho, matl_c)
+            if curved:
+                kurv_y, kurv_x = (float(v) for v in curv_pairs[geom // nz])
+                value_key = value_key + (kurv_y, kurv_x, geom % nz)
         row = expression_cache.get(value_key)
         if row is None:
             if key < 0:
                 heatflow = expression.linear_expression(0.0)
                 time_expression = -(T555p - T555m)
+            elif curved:
+                # reference :410-452: areas instead of 1/length, balance times the volume
+                (be_m55, be_p55, be_5m5, be_5p5, be_55m, be_55p) = bnd
+                kz = geom % nz
+                dy_top = (1.0 + kz * kurv_y * dz) * dy
+                dy_bot = (1.0 + (kz + 1) * kurv_y * dz) * dy
+                dy_m = np.mean((dy_top, dy_bot))
+                dx_top = (1.0 + kz * kurv_x * dz) * dx
+                dx_bot = (1.0 + (kz + 1) * kurv_x * dz) * dx
+                dx_m = np.mean((dx_top, dx_bot))
+                volume = np.abs(dx_m * dy_m * dz)
+                eb = curved_boundaries.get((dy_m, dx_m))
+                if eb is None:      # plug-ins evaluated with this layer's mean edge lengths (reference: symbolic dy, dx)
+                    eb = curved_boundaries[(dy_m, dx_m)] = evaluate_boundaries(boundaries, dz, dy_m, dx_m)
+                heatflow = (
+                    (shift_expression(eb[be_m55][0], (-.5, 0, 0)) * (dx_top * dy_top) - shift_expression(eb[be_p55][0], (+.5, 0, 0)) * (dx_bot * dy_bot)) +
+                    (shift_expression(eb[be_5m5][1], (0, -.5, 0)) - shift_expression(eb[be_5p5][1], (0, +.5, 0))) * (dx_m * dz) +
+                    (shift_expression(eb[be_55m][2], (0, 0, -.5)) - shift_expression(eb[be_55p][2], (0, 0, +.5))) * (dy_m * dz) +
+                    volumetric_source * volume)
+                heatflow = subst_thermal_conductivity(heatflow, k_params)
+                time_expression = -(T555p - T555m) * matl_rho * matl_c * volume * (1.0 / dt)
             else:
                 (be_m55, be_p55, be_5m5, be_5p5, be_55m, be_55p) = bnd
                 heatflow = (

@@ -398,6 +398,7 @@ class DistPlan(object):
 
 def setup(z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric,
           material_elements, boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements,
+          top_surface_y_curvatures=None, top_surface_x_curvatures=None, unaligned_anisotropic=False,
           group=None, device=None, plan_class=DistPlan):
     """Distributed counterpart of ``heatsim2_b200.setup``: same GLOBAL problem
     description on every rank; returns ``(ADI_params, ADI_steps)`` whose plan
@@ -410,8 +411,10 @@ def setup(z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumet
     k0, k1 = slab_range(nz, rank, world)
     class_id, coefs, volume_array, vol = crank_nicolson.compile_problem(
         z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric, material_elements,
-        boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements, device=device)
-    plan = AdiPlan((k1 - k0, ny, nx), None, coefs, dt, volume_array, volumetric_elements=vol[k0:k1],
+        boundary_z_elements, boundary_y_elements, boundary_x_elements, volumetric_elements,
+        top_surface_y_curvatures, top_surface_x_curvatures, unaligned_anisotropic, device=device)
+    slab_volume = volume_array[k0:k1] if np.ndim(volume_array) > 0 else volume_array    # per-cell volumes in curved mode
+    plan = AdiPlan((k1 - k0, ny, nx), None, coefs, dt, slab_volume, volumetric_elements=vol[k0:k1],
                    materials=materials, slab=(k0, class_id))
     (ADI_params, ADI_steps) = alternatingdirection.adi_setup((nz, ny, nx), volume_array)
     ADI_params.plan = plan_class(plan, group)

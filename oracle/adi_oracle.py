@@ -60,7 +60,7 @@ class OracleProblem(object):
 
     def __init__(self, z0, y0, x0, dz, dy, dx, nz, ny, nx, dt, materials, boundaries, volumetric,
                  material_elements, boundary_z_elements, boundary_y_elements, boundary_x_elements,
-                 volumetric_elements):
+                 volumetric_elements, top_surface_y_curvatures=None, top_surface_x_curvatures=None):
         self.shape = (nz, ny, nx)
         self.dt = dt
         self.d = (dz, dy, dx)
@@ -73,6 +73,24 @@ class OracleProblem(object):
         # capacity term  rho*c*(1/dt)   (crank_nicolson.pyx:378)
         self.M = np.where(fixed, 1.0, rhoc[me] * (1.0 / dt))
         self.D = np.where(fixed, 0.0, 1.0)
+        # curved-surface mode (crank_nicolson.pyx:388-458): the balance is multiplied
+        # through by the cell volume and every face flux by the face's own area
+        curved = top_surface_y_curvatures is not None or top_surface_x_curvatures is not None
+        area = None
+        if curved:
+            kk = np.arange(nz, dtype=np.float64)[:, None, None]
+            cy = np.asarray(top_surface_y_curvatures, dtype=np.float64)[None, :, :]
+            cx = np.asarray(top_surface_x_curvatures, dtype=np.float64)[None, :, :]
+            dy_top, dy_bot = (1.0 + kk * cy * dz) * dy, (1.0 + (kk + 1) * cy * dz) * dy
+            dx_top, dx_bot = (1.0 + kk * cx * dz) * dx, (1.0 + (kk + 1) * cx * dz) * dx
+            dy_mean, dx_mean = 0.5 * (dy_top + dy_bot), 0.5 * (dx_top + dx_bot)
+            vol = np.abs(dx_mean * dy_mean * dz)
+            self.volume = np.where(fixed, 0.0, vol)          # volume_array stays 0 in FIXED cells
+            self.M = np.where(fixed, 1.0, rhoc[me] * vol * (1.0 / dt))
+            self.D = np.where(fixed, 0.0, vol)
+            area = {(Z, -1): dx_top * dy_top, (Z, +1): dx_bot * dy_bot,
+                    (Y, -1): dx_mean * dz, (Y, +1): dx_mean * dz, (X, -1): dy_mean * dz, (X, +1): dy_mean * dz}
+            length = {Z: dz * np.ones(self.shape), Y: dy_mean * np.ones(self.shape), X: dx_mean * np.ones(self.shape)}
         faces = {Z: np.asarray(boundary_z_elements), Y: np.asarray(boundary_y_elements), X: np.asarray(boundary_x_elements)}
         kinds = [_boundary_kind(b) for b in boundaries]
         self.g = {}
@@ -100,7 +118,13 @@ class OracleProblem(object):
                     sel = bcls == b
                     if not sel.any() or kind == "insulating":
                         continue
-                    if kind in ("conducting", "anisotropic"):
+                    if curved:
+                        # flux per unit area times the face area (no division by the cell size)
+                        if kind in ("conducting", "anisotropic"):
+                            val = ((k_self + k_nbr) * 0.5) * (1.0 / length[axis]) * area[(axis, side)]
+                        else:
+                            val = float(boundaries[b][1]) * area[(axis, side)]
+                    elif kind in ("conducting", "anisotropic"):
                         val = ((k_self + k_nbr) * 0.5) * (1.0 / d) * (1.0 / d)
                     else:  # thin layer: q = -h dT, divided by the cell size
                         val = np.full(self.shape, float(boundaries[b][1]) * (1.0 / d))
@@ -134,7 +158,8 @@ class OracleProblem(object):
                     out[ve == idx] = entry[3]
             elif kind == IMPULSE_POINT_SOURCE_JOULES:
                 if t == entry[1]:
-                    out[ve == idx] = entry[2] / (self.volume * dt)
+                    sel = ve == idx
+                    out[sel] = entry[2] / ((self.volume[sel] if np.ndim(self.volume) else self.volume) * dt)
             elif kind == SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE:
                 (_, t_imp, direc, offset, z_ndgrid, ddz, jpm2, clen) = entry
                 if t == t_imp:
@@ -210,8 +235,8 @@ class OracleProblem(object):
 
 
 def setup(*args):
-    """Same positional arguments as heatsim2.setup (crank_nicolson.pyx:128-142,
-    without the curvature options)."""
+    """Same positional arguments as heatsim2.setup (crank_nicolson.pyx:128-142),
+    including the two optional top-surface curvature arrays."""
     return OracleProblem(*args)
 
 

@@ -36,6 +36,7 @@ CASES = {
     "sources_demo": ("sources_demo", dict(), (1, 2, 3, 4, 5, 6)),
     "line_1d": ("uniform_slab", dict(shape=(1, 1, 40), nsteps=5), (1, 5)),
     "plane_2d": ("uniform_slab", dict(shape=(1, 24, 20), nsteps=5), (1, 5)),
+    "c6_curved_plate": ("curved_plate", dict(nz=24, ny=20, nx=28, nsteps=12), (1, 3, 12)),
 }
 
 
@@ -43,7 +44,10 @@ def main():
     ref = ref_loader.load()
     if ref is None:
         raise SystemExit("reference not built: run python oracle/build_ref.py first")
+    only = set(sys.argv[1:])          # optional: names of the cases to (re)generate
     for case, (pname, kwargs, steps) in CASES.items():
+        if only and case not in only:
+            continue
         prob = problems.ALL[pname](ref, **kwargs)
         P, S = ref_loader.quiet_setup(ref, *prob["setup_args"])
         T = np.array(prob["T0"], dtype=np.float64)

@@ -151,5 +151,33 @@ def sources_demo(hs, nz=12, ny=10, nx=14, seed=3):
     return _pack(hs, (dz, dy, dx, z, y, x), dt, materials, boundaries, volumetric, (me, bz, by, bx, ve), T0, 6)
 
 
-ALL = {"steelonfoam": steelonfoam, "uniform_slab": uniform_slab, "steelonwater": steelonwater,
+def curved_plate(hs, nz=24, ny=20, nx=28, nsteps=12, seed=21):
+    """Curved-surface mode (crank_nicolson.pyx:388-458): steel on foam under a
+    top surface with curvature 1/(50 mm) about x everywhere and two different
+    curvatures about y (concave left half, convex right half), so the cell
+    geometry - and with it the equation class - changes with depth.  Flash on
+    layer 0 at t=0, a point source (Joules; divides by the per-cell volume) at
+    t=2*dt, an insulating gap on the interface."""
+    dt = 0.01
+    (dz, dy, dx, z, y, x, zgrid, ygrid, xgrid, z_bnd, y_bnd, x_bnd) = hs.build_grid(
+        0, 10.8e-3, nz, -0.05, 0.05, ny, -.06, .06, nx)[:12]
+    fi = nz // 3
+    materials = ((hs.TEMPERATURE_COMPUTE,) + STEEL, (hs.TEMPERATURE_COMPUTE,) + FOAM)
+    boundaries = ((hs.boundary_conducting,), (hs.boundary_insulating,))
+    volumetric = ((hs.NO_SOURCE,), (hs.IMPULSE_SOURCE, 0.0, 10e3 / dz), (hs.IMPULSE_POINT_SOURCE_JOULES, 2 * dt, 2e-3))
+    me, bz, by, bx, ve = hs.zero_elements(nz, ny, nx)
+    me[fi:, :, :] = 1
+    _insulate_outer(bz, by, bx)
+    bz[fi, ny // 4: ny // 2, nx // 4: nx // 2] = 1
+    ve[0, :, :] = 1
+    ve[2, ny // 2, nx // 3] = 2
+    cy = np.full((ny, nx), 1.0 / 50e-3)
+    cx = np.where(np.arange(nx)[None, :] < nx // 2, 1.0 / 80e-3, -1.0 / 200e-3) * np.ones((ny, nx))
+    T0 = np.random.default_rng(seed).random((nz, ny, nx))
+    d = _pack(hs, (dz, dy, dx, z, y, x), dt, materials, boundaries, volumetric, (me, bz, by, bx, ve), T0, nsteps)
+    d["setup_args"] = d["setup_args"] + (cy, cx)
+    return d
+
+
+ALL = {"curved_plate": curved_plate, "steelonfoam": steelonfoam, "uniform_slab": uniform_slab, "steelonwater": steelonwater,
        "composite": composite, "sources_demo": sources_demo}

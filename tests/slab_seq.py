@@ -21,7 +21,8 @@ def run(hs, prob, world, nsteps):
     class_id, coefs, volume_array, vol = crank_nicolson.compile_problem(*a, device=dev)
     plans = []
     for r in range(world):
-        pl = AdiPlan((h, ny, nx), None, coefs, dt, volume_array, volumetric_elements=vol[r * h:(r + 1) * h],
+        slab_volume = volume_array[r * h:(r + 1) * h] if np.ndim(volume_array) > 0 else volume_array
+        pl = AdiPlan((h, ny, nx), None, coefs, dt, slab_volume, volumetric_elements=vol[r * h:(r + 1) * h],
                      materials=materials, slab=(r * h, class_id))
         pl.ensure_device(dev)
         plans.append(pl)

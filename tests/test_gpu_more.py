@@ -124,6 +124,7 @@ def test_device_resident_loop_with_observation(hs):
     ("uniform_slab", dict(shape=(64, 40, 50)), 8, 3),
     ("composite", dict(nz=64, ny=32, nx=32, ply=8), 2, 4),
     ("steelonwater", dict(nz=64, ny=40, nx=48), 2, 4),
+    ("curved_plate", dict(nz=32, ny=20, nx=28), 2, 4),
 ])
 def test_slab_kernels_on_one_gpu(hs, name, kwargs, world, nsteps):
     """The kernels of the multi-GPU z-slab path, slabs run one after the other

@@ -46,6 +46,7 @@ def test_golden_vectors(hs, case):
     ("steelonwater", dict(nz=40, ny=40, nx=48, nsteps=5)),
     ("composite", dict(nz=32, ny=64, nx=64, nsteps=5)),
     ("sources_demo", dict()),
+    ("curved_plate", dict()),
 ])
 def test_single_steps_vs_oracle(hs, name, kwargs):
     """Every step restarted from the oracle's state: <= 1e-12."""

@@ -19,6 +19,7 @@ CASES = [
     ("steelonwater", dict(nz=24, ny=40, nx=48)),
     ("composite", dict(nz=16, ny=12, nx=20, ply=4)),
     ("sources_demo", dict()),
+    ("curved_plate", dict(nz=12, ny=10, nx=12)),
     ("uniform_slab", dict(shape=(1, 1, 17))),
 ]
 
@@ -88,7 +89,7 @@ def test_few_classes_and_lines_on_baseline_geometries():
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("name,kwargs", CASES[:5])
+@pytest.mark.parametrize("name,kwargs", CASES[:6])
 def test_matrices_equal_reference(name, kwargs):
     ref = ref_loader.load()
     Pr, Sr = ref_loader.quiet_setup(ref, *problems.ALL[name](ref, **kwargs)["setup_args"])
