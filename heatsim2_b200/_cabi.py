@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhs2b200.so")
+# HS2_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("HS2_B200_LIB") or os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4

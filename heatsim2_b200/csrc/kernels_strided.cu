@@ -255,17 +255,24 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     HS2_MARK(5);
     if (live) {
       if (FINAL) {
-        // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
+        // T_in in batches of 8 rows, software-pipelined: the loads of batch g+1
+        // are in flight while batch g is added and stored
         const double *ti = Tin + off;
         double *to = Tout + off;
+        // (requesting the first batch before the back substitution measured slower: 0.68 vs 0.63 ms)
+        double tin[2][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tin[0][q] = (q < rows) ? ti[(int64_t)q * stride] : 0.0;
 #pragma unroll
         for (int g = 0; g < M; g += 8) {
-          double tin[8];
+          if (g + 8 < M) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) tin[q] = (g + q < rows) ? ti[(int64_t)(g + q) * stride] : 0.0;
+            for (int q = 0; q < 8; ++q)
+              tin[((g >> 3) + 1) & 1][q] = (g + 8 + q < rows) ? ti[(int64_t)(g + 8 + q) * stride] : 0.0;
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (g + q < rows) to[(int64_t)(g + q) * stride] = tin[q] + v[g + q];
+            if (g + q < rows) to[(int64_t)(g + q) * stride] = tin[(g >> 3) & 1][q] + v[g + q];
         }
       } else {
         double *dst = data + off;
@@ -531,14 +538,19 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
       chunk_fwd<M, true>(v, tg, M, &last);
       chunk_bwd<M, true>(v, tg, M, alpha, E);
     }
-    // T_in in batches of 8 rows: 8 loads in flight, then 8 adds + stores
+    // T_in in batches of 8 rows, software-pipelined: the loads of batch g+1 are
+    // in flight while batch g is added and stored
+    double tin[2][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tin[0][q] = Tin[off + (int64_t)q * stride];
 #pragma unroll
     for (int gb = 0; gb < M; gb += 8) {
-      double tin[8];
+      if (gb + 8 < M) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) tin[q] = Tin[off + (int64_t)(gb + q) * stride];
+        for (int q = 0; q < 8; ++q) tin[((gb >> 3) + 1) & 1][q] = Tin[off + (int64_t)(gb + 8 + q) * stride];
+      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[q] + v[gb + q];
+      for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[(gb >> 3) & 1][q] + v[gb + q];
     }
   }
 }
