@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise ncu outputs into tracked text files under profiles/.
 
-  python profiles/summarize.py launches gpurun_out/launches_r01.csv  > profiles/launches_r01.md
+  python profiles/summarize.py launches gpurun_out/launches_r01.csv  > profiles/launches_r01.md   (r01b = end of round 1)
   python profiles/summarize.py full gpurun_out/prof_r01.ncu-rep       > profiles/kernels_r01.md  (also writes traffic.json)
 """
 import collections
@@ -24,7 +24,8 @@ def short(name):
             how = "TMA prefetch" if args[3] in ("1", "true") else "cp.async prefetch"
             return "strided_sweep_tma (%s, persistent, %s)" % ("z" if final else "y", how)
         return "strided_sweep (%s, register loads)" % ("z" if final else "y")
-    for key, lab in (("sweep_x_kernel", "sweep_x_kernel (x: RHS + solve)"), ("sweep_x_march", "sweep_x_march (x, z-marching)"),
+    for key, lab in (("sweep_xf_kernel", "sweep_xf_kernel (sweep_x: 5-point RHS + folded solve)"),
+                     ("sweep_x_kernel", "sweep_x_kernel (x: RHS + solve)"),
                      ("z_forward", "z_forward (slab)"), ("z_backward", "z_backward (slab)"),
                      ("rhs_kernel", "rhs_kernel (fallback)"), ("thomas_kernel", "thomas_kernel (fallback)")):
         if key in name:
