@@ -330,7 +330,7 @@ def main():
     if args.gpus == 1:
         return run_b200_single(args)
     from heatsim2_b200 import dist_bench
-    return dist_bench.run(args, grid_for(args.gpus, args.grid), workload_name)
+    return dist_bench.run(args, grid_for(args.gpus, args.grid), workload_name, ClockSampler)
 
 
 if __name__ == "__main__":

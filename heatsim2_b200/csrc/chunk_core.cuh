@@ -209,16 +209,3 @@ __device__ __forceinline__ void chunk_bwd(double (&v)[M], const TAB &tb, int row
     }
   }
 }
-
-// E_p from the interleaved (yf, yl) values of the line's chunks, 8-byte loads
-// of the inverse interface operator row (shared window address or global)
-__device__ __forceinline__ double chunk_interface_s(uint32_t ge_s, const double *Y, int P, int ld, int w, int p, int band) {
-  double e0 = 0.0, e1 = 0.0;
-  const int q0 = max(0, p - band), q1 = min(P - 1, p + band);
-#pragma unroll 4
-  for (int q = q0; q <= q1; ++q) {
-    e0 = fma(TabShared::ld(ge_s, 2 * q), Y[(2 * q) * ld + w], e0);
-    e1 = fma(TabShared::ld(ge_s, 2 * q + 1), Y[(2 * q + 1) * ld + w], e1);
-  }
-  return e0 + e1;
-}

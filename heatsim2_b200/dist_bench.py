@@ -12,7 +12,7 @@ METRIC = "ADI cell-updates/s (float64)"
 UNIT = "cell-updates/s"
 
 
-def run(args, shape, workload_name):
+def run(args, shape, workload_name, clock_sampler=None):
     import heatsim2_b200 as hs
     from heatsim2_b200 import _cabi, dist as hdist
     import problems
@@ -46,10 +46,16 @@ def run(args, shape, workload_name):
         hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
         Ta, Tb = Tb, Ta
         it += 1
+    sampler = None
+    if clock_sampler is not None and rank == 0:      # nvidia-smi clocks / throttle reasons of rank 0's GPU during the timed region
+        sampler = clock_sampler(local)
+        sampler.start()
+        time.sleep(0.3)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
@@ -57,7 +63,9 @@ def run(args, shape, workload_name):
         it += 1
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     dist.barrier()
+    clocks = sampler.stop(t_begin, t_end) if sampler is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
@@ -123,7 +131,7 @@ def run(args, shape, workload_name):
                 "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_global * 8,
                         "d2h_bytes_per_step": n_global * 8, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "api": "per rank: pinned host slab -> device, heatsim2_b200.run_adi_steps (dist plan), device -> pinned host"},
-                "gpu_launches": args.steps * (8 if dplan._px is not None else 4) * world}
+                "gpu_launches": args.steps * (8 if dplan._px is not None else 4) * world, "clocks": clocks}
         print(json.dumps(line))
     dplan.check()
     dplan.close()
