@@ -309,7 +309,8 @@ def run_b200_single(args):
             "data": "synthetic",
             "config": {"workload": workload_name(shape), "grid": list(shape), "cells": n,
                        "l2": "inputs larger than L2 (3 arrays of %.2f GB vs 126 MB)" % (n * 8 / 1e9),
-                       "classes": plan.n_classes, "unique_lines": list(plan.n_unique), "setup_s": setup_s},
+                       "classes": plan.n_classes, "unique_lines": list(plan.n_unique), "setup_s": setup_s,
+                       "x_kernel": plan.x_kernel},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": args.steps * plan.launches_per_step, "clocks": clocks}
     print(json.dumps(line))

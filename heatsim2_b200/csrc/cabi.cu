@@ -62,6 +62,12 @@ int hs2_plan_launches_per_step(const hs2_plan *plan) {
   return (hs2_tile_xf_supported(plan) ? 1 : 2) + 2;
 }
 
+int hs2_plan_x_kernel(const hs2_plan *plan) {
+  if (!plan) return -1;
+  if (!hs2_tile_xf_supported(plan)) return HS2_XK_WHOLE_LINE;
+  return hs2_tile_xm_supported(plan) ? HS2_XK_MARCH : HS2_XK_FOLD;
+}
+
 int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src, const double *d_halo_lo,
                 const double *d_halo_hi, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");

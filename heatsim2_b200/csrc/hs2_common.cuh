@@ -68,3 +68,6 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                       const double *halo_hi, int part, cudaStream_t st);
+// kernels_xm.cu - z-marching variant of the folded x sweep (HS2_FLAG_X_MARCH); *done = false: not applicable
+int hs2_tile_sweep_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *done);
+bool hs2_tile_xm_supported(const hs2_plan *p);

@@ -178,6 +178,9 @@ def interface_band(GE, tol=1e-16):
     return int((dist[None, :, :] * sig).max()) if sig.any() else 0
 
 
+X_KERNEL_DEFAULT = "fold"      # "march" once measured faster on B200 (profiles/NOTES_r01.md)
+
+
 class AdiPlan(object):
     """One problem (or one z-slab of it) compiled for the CUDA library.
 
@@ -218,6 +221,10 @@ class AdiPlan(object):
         self._handle = None
         # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
         self.flags = 1 if os.environ.get("HS2_FORCE_FALLBACK", "0") == "1" else 0
+        # HS2_X_KERNEL=march: z-marching shared-memory-ring x kernel (HS2_FLAG_X_MARCH) for
+        # source-free whole-grid sweeps; =fold: kernels_xf.cu everywhere
+        if os.environ.get("HS2_X_KERNEL", X_KERNEL_DEFAULT) == "march":
+            self.flags |= 2
         self._bufs = {}
         self._vol_dev = None
         self._vol_key = None
@@ -283,6 +290,12 @@ class AdiPlan(object):
         """kernels launched by one hs2_step"""
         self.ensure_device()
         return int(_cabi.lib().hs2_plan_launches_per_step(self._handle))
+
+    @property
+    def x_kernel(self):
+        """'whole-line', 'fold' or 'march': the kernel a source-free hs2_sweep_x of this plan runs"""
+        self.ensure_device()
+        return ("whole-line", "fold", "march")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
 
     @property
     def n_unique(self):

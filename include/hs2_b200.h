@@ -106,6 +106,7 @@ typedef struct hs2_plan_desc {
 } hs2_plan_desc;
 
 #define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
+#define HS2_FLAG_X_MARCH 2        /* x sweep: z-marching shared-memory-ring kernel for source-free whole-grid sweeps */
 
 typedef struct hs2_plan hs2_plan;
 
@@ -131,6 +132,14 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out);
 int hs2_plan_destroy(hs2_plan *plan);
 /* number of kernels one hs2_step launches with this plan                     */
 int hs2_plan_launches_per_step(const hs2_plan *plan);
+
+/* which kernel a source-free whole-grid hs2_sweep_x of this plan runs:
+ * whole-line global-memory fallback (rhs + Thomas), folded tile kernel, or
+ * the z-marching shared-memory-ring kernel (HS2_FLAG_X_MARCH)                */
+#define HS2_XK_WHOLE_LINE 0
+#define HS2_XK_FOLD 1
+#define HS2_XK_MARCH 2
+int hs2_plan_x_kernel(const hs2_plan *plan);
 
 /* One ADI time step = run_adi_steps (alternatingdirection_c_pyx.pyx:287-416).
  *   d_T_in   [nz][ny][nx]  field at t - dt/2

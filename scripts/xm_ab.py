@@ -1,0 +1,85 @@
+"""A/B of the two x-sweep kernels on one GPU (same process, same field):
+kernels_xf.cu (fold) vs kernels_xm.cu (march), x-sweep alone and whole step,
+plus the march kernel's plane-range length.  Writes gpurun_out/xm_ab.json.
+
+    python scripts/xm_ab.py [grid] [reps]
+"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import torch
+
+import heatsim2_b200 as hs
+from heatsim2_b200 import _cabi
+import problems
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    grid = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    lib = _cabi.lib()
+    out = {"grid": grid, "reps": reps, "runs": []}
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    T = torch.rand((grid, grid, grid), dtype=torch.float64, device=dev, generator=g)
+    T2 = torch.empty_like(T)
+    W = {}
+    for chunk in ("32", "16"):
+        os.environ["HS2_CHUNK_X"] = chunk
+        prob = problems.uniform_slab(hs, shape=(grid, grid, grid), random_T0=False)
+        P, S = hs.setup(*prob["setup_args"])
+        plan = P.plan
+        for flags, name in ((0, "fold"), (2, "march")):
+            plan.flags = flags
+            plan.release()
+            plan.ensure_device(dev)
+            work = plan._buf("work")
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            krs = ("32",) if name == "fold" else ("32", "16", "64", "128")
+            for kr in krs:
+                os.environ["HS2_XM_KR"] = kr
+                try:
+                    x_ms = timed(lambda: _cabi.check(lib.hs2_sweep_x(plan._handle, T.data_ptr(), work.data_ptr(), None, None, None, st)), reps)
+                    key = (chunk, name)
+                    if key not in W:
+                        W[key] = work.clone()
+                    step_ms = timed(lambda: _cabi.check(lib.hs2_step(plan._handle, T.data_ptr(), T2.data_ptr(), work.data_ptr(),
+                                                                      None, None, None, st)), reps)
+                    rec = {"chunk_x": int(chunk), "kernel": name, "x_kernel": plan.x_kernel, "KR": int(kr), "x_ms": x_ms,
+                           "step_ms": step_ms, "G_cell_updates_per_s": grid ** 3 / step_ms / 1e6}
+                except Exception as exc:                      # keep going: the other variant still gets measured
+                    rec = {"chunk_x": int(chunk), "kernel": name, "KR": int(kr), "error": str(exc)[:300]}
+                print(json.dumps(rec), flush=True)
+                out["runs"].append(rec)
+        if (chunk, "fold") in W and (chunk, "march") in W:
+            a, b = W[(chunk, "fold")], W[(chunk, "march")]
+            err = float((a - b).abs().max() / a.abs().max())
+            rec = {"chunk_x": int(chunk), "march_vs_fold_relerr": err, "bitwise_equal": bool(torch.equal(a, b))}
+            print(json.dumps(rec), flush=True)
+            out["runs"].append(rec)
+        del plan, P, S
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "xm_ab.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

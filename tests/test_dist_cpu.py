@@ -1,4 +1,4 @@
-"""Multi-GPU host logic on CPU ranks (gloo, world_size 2 and 4): slab
+"""Multi-GPU host logic on CPU ranks (gloo, world_size 2, 4, 6 and 8): slab
 partition, halo exchange, all-gather layout and the global z-line tables, with
 the kernels replaced by their numpy transcriptions (tests/emul.py).  The slab
 results must equal the oracle / the single-domain run."""
@@ -68,6 +68,9 @@ def _run(world, name, kwargs, nsteps, env=None, info=None):
     (4, "steelonfoam", dict(nz=64, ny=10, nx=12)),
     (2, "composite", dict(nz=32, ny=12, nx=16, ply=4)),
     (2, "steelonwater", dict(nz=48, ny=20, nx=24)),
+    # BASELINE configs[4] recipe (uniform steel slab, random T0) on 8 ranks: strongly
+    # implicit z-lines, so the interface band spans several 8-plane slabs
+    (8, "uniform_slab", dict(shape=(64, 10, 12))),
 ])
 def test_slabs_match_oracle(world, name, kwargs):
     import heatsim2_b200 as hs
