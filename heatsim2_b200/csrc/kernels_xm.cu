@@ -53,6 +53,8 @@ struct XmGeom {
   int Sr;           // row pitch of the solve buffer
   int tab_in_smem;  // factor tables of the block's line class in shared memory
   int ge_in_smem;   // ... and its interface-operator rows
+  int buf_alias;    // solve buffer lives in the slice of plane k-1
+  int RPT;          // rows per thread in phases 1 and 3 (2 or 4)
   int KR;           // planes per work item
   int tiles_y;
   int n_items;
@@ -81,19 +83,19 @@ __device__ __forceinline__ void xm_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
-template <int M, typename CID>
-__global__ void __launch_bounds__(256, 1)
+template <int M, int RPT, typename CID>
+__global__ void __launch_bounds__(512, 1)
 sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ Wout, const CID *__restrict__ cid,
                 const double *__restrict__ coef_g, int n_classes, int coef_in_smem,
                 const uint32_t *__restrict__ line_id, const double *__restrict__ tab, int pitch,
                 const double *__restrict__ GE, int nz, int ny, int nx, int P, int band, XmGeom g) {
   constexpr int R = HS2_XR;
   constexpr int RW = R + 2;
-  constexpr int NC = M >= 32 ? 2 : 1;   // column pairs per thread: 2 * (R*P) * NC >= nx
+  constexpr int RG = R / RPT;           // row groups of phases 1 and 3
   extern __shared__ __align__(128) unsigned char xm_raw[];
   double *slots = reinterpret_cast<double *>(xm_raw);                          // [4][slot_stride]
-  double *buf = slots + (size_t)XM_SLOTS * g.slot_stride;                      // [R][Sr]
-  double *Y = buf + R * g.Sr;                                                  // [2P][R]
+  double *buf_own = slots + (size_t)XM_SLOTS * g.slot_stride;                  // [R][Sr] unless aliased
+  double *Y = buf_own + (g.buf_alias ? 0 : R * g.Sr);                          // [2P][R]
   double *Es = Y + 2 * P * R;                                                  // [P][R]
   double *cfs = Es + P * R;                                                    // [n_classes][8]
   double *s_tab = cfs + (coef_in_smem ? n_classes * HS2_COEF_STRIDE : 0);      // [PLANES][P][M+TP]
@@ -137,30 +139,27 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
   }
   __syncthreads();
 
-  // phase-2 role of this thread: chunk pc of line r2
+  // phase-2 role (threads 0 .. R*P-1): chunk pc of line r2
+  const bool solver = tid < R * P;
   const int r2 = tid % R;
-  const int p2 = tid / R;
-  const int pc = p2 < P ? p2 : P - 1;
+  const int p2 = solver ? tid / R : P - 1;
+  const int pc = p2;
   const int c0 = pc * M;
   const int rows = min(M, nx - c0);
   const bool full = rows == M;
-  double *mine = buf + r2 * g.Sr + pc * (M + XM_PAD);
+  const int mine_off = r2 * g.Sr + pc * (M + XM_PAD);
   TabShared ts;
   ts.a = smem_u32(s_tab + pc * (M + XM_TP));
   ts.pitch_b = (uint32_t)(P * (M + XM_TP)) * 8u;
 
-  // phase-1/3 role: column pairs ic[c], ic[c]+1
-  int ic[NC], so[NC], bo[NC];
-  bool cv[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int i = 2 * tid + 2 * nthreads * c;
-    cv[c] = i < nx;
-    ic[c] = cv[c] ? i : 0;
-    const int xb = ic[c] / BX;
-    so[c] = xb * g.box_stride + (ic[c] - xb * BX);
-    bo[c] = ic[c] + XM_PAD * (ic[c] / M);
-  }
+  // phase-1/3 role (threads 0 .. RG*nx/2-1): column pair ic, ic+1 of rows r0 .. r0+RPT-1
+  const int cpt = nx >> 1;
+  const int rg = tid / cpt;
+  const bool stencil = rg < RG;
+  const int ic = stencil ? 2 * (tid - rg * cpt) : 0;
+  const int r0 = stencil ? rg * RPT : 0;
+  const int so = (ic / BX) * g.box_stride + (ic % BX);
+  const int bo = ic + XM_PAD * (ic / M);
 
   const uint32_t slice_bytes = (uint32_t)g.NXB * RW * BX * sizeof(double);
   uint32_t phase_bits = 0;   // bit s: parity the next wait on slot s uses
@@ -194,30 +193,28 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
       for (int q = 0; q < 3; ++q)
         if (needed(q)) issue(q);
     }
-    // window rows of the centre slice, clamped to the plane like kernels_xf.cu
-    int rq[RW];
+    // window rows r0-1 .. r0+RPT of the centre slice, clamped to the plane like kernels_xf.cu
+    int rq[RPT + 2];
 #pragma unroll
-    for (int q = 0; q < RW; ++q) {
-      int j = j0 + q - 1;
+    for (int q = 0; q < RPT + 2; ++q) {
+      int j = j0 + r0 + q - 1;
       j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
       rq[q] = (j - (j0 - 1)) * BX;
     }
-    // class ids of plane ka (column pairs of rows j0.., clamped)
-    uint32_t idc[NC][R], idn[NC][R];
+    // class ids of plane ka (this thread's column pair, rows clamped)
+    uint32_t idc[RPT], idn[RPT];
     {
       const CID *cidk = cid + (int64_t)ka * plane;
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int j = min(j0 + r, ny - 1);
-          const CID *a = cidk + ((int64_t)j * nx + ic[c]);
-          if (sizeof(CID) == 1)
-            idc[c][r] = *reinterpret_cast<const uint16_t *>(a);
-          else
-            idc[c][r] = *reinterpret_cast<const uint32_t *>(a);
-          idn[c][r] = 0;
-        }
+      for (int r = 0; r < RPT; ++r) {
+        const int j = min(j0 + r0 + r, ny - 1);
+        const CID *a = cidk + ((int64_t)j * nx + ic);
+        if (sizeof(CID) == 1)
+          idc[r] = *reinterpret_cast<const uint16_t *>(a);
+        else
+          idc[r] = *reinterpret_cast<const uint32_t *>(a);
+        idn[r] = 0;
+      }
     }
 
     for (int it = 0; it < n_it; ++it) {
@@ -228,16 +225,14 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
       if (it + 1 < n_it) {   // class ids of the next plane: in flight during this one
         const CID *cidk = cid + kbase + plane;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int j = min(j0 + r, ny - 1);
-            const CID *a = cidk + ((int64_t)j * nx + ic[c]);
-            if (sizeof(CID) == 1)
-              idn[c][r] = *reinterpret_cast<const uint16_t *>(a);
-            else
-              idn[c][r] = *reinterpret_cast<const uint32_t *>(a);
-          }
+        for (int r = 0; r < RPT; ++r) {
+          const int j = min(j0 + r0 + r, ny - 1);
+          const CID *a = cidk + ((int64_t)j * nx + ic);
+          if (sizeof(CID) == 1)
+            idn[r] = *reinterpret_cast<const uint16_t *>(a);
+          else
+            idn[r] = *reinterpret_cast<const uint32_t *>(a);
+        }
       }
       HS2_MARK(8);
       if (it == 0) {
@@ -249,105 +244,115 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
       const double *Cn = slots + (size_t)((it + 1) & (XM_SLOTS - 1)) * g.slot_stride;
       const double *Lo = k > 0 ? slots + (size_t)(it & (XM_SLOTS - 1)) * g.slot_stride : Cn;
       const double *Hi = k + 1 < nz ? slots + (size_t)((it + 2) & (XM_SLOTS - 1)) * g.slot_stride : Cn;
+      // solve buffer: its own region, or (buf_alias) the slice of plane k-1, which
+      // nobody reads after phase 1 and no copy targets before the next iteration
+      double *buf = g.buf_alias ? slots + (size_t)(it & (XM_SLOTS - 1)) * g.slot_stride : buf_own;
 
       // ------------------------------------------------ phase 1: 2T + q
+      double2 outv[RPT];
+      if (stencil) {
+        const double *cc = Cn + so;
+        const double *zl = Lo + so;
+        const double *zh = Hi + so;
+        double2 tc[RPT + 2];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (cv[c]) {
-          const double *cc = Cn + so[c];
-          const double *zl = Lo + so[c];
-          const double *zh = Hi + so[c];
-          double *bcol = buf + bo[c];
-          double2 tc[RW];
+        for (int q = 0; q < RPT + 2; ++q) tc[q] = *reinterpret_cast<const double2 *>(cc + rq[q]);
+        int last_id = -1;
+        double2 cy = make_double2(0, 0), cz = cy;
 #pragma unroll
-          for (int q = 0; q < RW; ++q) tc[q] = *reinterpret_cast<const double2 *>(cc + rq[q]);
-          int last_id = -1;
-          double2 cy = make_double2(0, 0), cz = cy;
+        for (int r = 0; r < RPT; ++r) {
+          const double2 zm = *reinterpret_cast<const double2 *>(zl + (r0 + r + 1) * BX);
+          const double2 zp = *reinterpret_cast<const double2 *>(zh + (r0 + r + 1) * BX);
+          const int q = r + 1;
+          const double2 t0 = tc[q];
+          const int id0 = sizeof(CID) == 1 ? (int)(idc[r] & 0xff) : (int)(idc[r] & 0xffff);
+          const int id1 = sizeof(CID) == 1 ? (int)((idc[r] >> 8) & 0xff) : (int)((idc[r] >> 16) & 0xffff);
+          double out[2];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const double2 zm = *reinterpret_cast<const double2 *>(zl + (r + 1) * BX);
-            const double2 zp = *reinterpret_cast<const double2 *>(zh + (r + 1) * BX);
-            const int q = r + 1;
-            const double2 t0 = tc[q];
-            const int id0 = sizeof(CID) == 1 ? (int)(idc[c][r] & 0xff) : (int)(idc[c][r] & 0xffff);
-            const int id1 = sizeof(CID) == 1 ? (int)((idc[c][r] >> 8) & 0xff) : (int)((idc[c][r] >> 16) & 0xffff);
-            double out[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int idc_e = e ? id1 : id0;
-              if (idc_e != last_id) {
-                const double2 *c2 = reinterpret_cast<const double2 *>(coef + idc_e * HS2_COEF_STRIDE);
-                cy = c2[1];
-                cz = c2[2];
-                last_id = idc_e;
-              }
-              const double tt = e ? t0.y : t0.x;
-              const double vym = e ? tc[q - 1].y : tc[q - 1].x;
-              const double vyp = e ? tc[q + 1].y : tc[q + 1].x;
-              const double vzm = e ? zm.y : zm.x;
-              const double vzp = e ? zp.y : zp.x;
-              double rr = cy.x * (vym - tt);
-              rr = fma(cy.y, vyp - tt, rr);
-              rr = fma(cz.x, vzm - tt, rr);
-              rr = fma(cz.y, vzp - tt, rr);
-              out[e] = fma(2.0, tt, rr);
+          for (int e = 0; e < 2; ++e) {
+            const int idc_e = e ? id1 : id0;
+            if (idc_e != last_id) {
+              const double2 *c2 = reinterpret_cast<const double2 *>(coef + idc_e * HS2_COEF_STRIDE);
+              cy = c2[1];
+              cz = c2[2];
+              last_id = idc_e;
             }
-            *reinterpret_cast<double2 *>(bcol + r * g.Sr) = make_double2(out[0], out[1]);
+            const double tt = e ? t0.y : t0.x;
+            const double vym = e ? tc[q - 1].y : tc[q - 1].x;
+            const double vyp = e ? tc[q + 1].y : tc[q + 1].x;
+            const double vzm = e ? zm.y : zm.x;
+            const double vzp = e ? zp.y : zp.x;
+            double rr = cy.x * (vym - tt);
+            rr = fma(cy.y, vyp - tt, rr);
+            rr = fma(cz.x, vzm - tt, rr);
+            rr = fma(cz.y, vzp - tt, rr);
+            out[e] = fma(2.0, tt, rr);
           }
+          outv[r] = make_double2(out[0], out[1]);
         }
+      }
+      if (g.buf_alias) __syncthreads();   // every read of slice k-1 is done before the solve buffer overwrites it
+      if (stencil) {
+        double *bcol = buf + bo;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) *reinterpret_cast<double2 *>(bcol + (r0 + r) * g.Sr) = outv[r];
       }
       HS2_MARK(1);
       __syncthreads();
 
       // ------------------------------------------------ phase 2: solve along x
+      double *mine = buf + mine_off;
       const bool tab_s = g.tab_in_smem && lid == lid_c;
       TabGlobal tg;
       tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + c0;
       tg.pitch = pitch;
       const double *ge = (tab_s && g.ge_in_smem) ? s_ge + pc * (2 * P + 2) : GE + ((int64_t)lid * P + pc) * (2 * P);
       double v[M];
+      if (solver) {
 #pragma unroll
-      for (int t = 0; t < M; t += 2) {
-        double2 x = make_double2(0.0, 0.0);
-        if (full || t < rows) x = *reinterpret_cast<const double2 *>(mine + t);
-        v[t] = x.x;
-        v[t + 1] = x.y;
-      }
-      double yf, last;
-      if (tab_s) {
-        if (full)
-          yf = chunk_fwd<M, true>(v, ts, M, &last);
-        else
-          yf = chunk_fwd<M, false>(v, ts, rows, &last);
-      } else {
-        if (full)
-          yf = chunk_fwd<M, true>(v, tg, M, &last);
-        else
-          yf = chunk_fwd<M, false>(v, tg, rows, &last);
-      }
-      if (p2 < P) {
+        for (int t = 0; t < M; t += 2) {
+          double2 x = make_double2(0.0, 0.0);
+          if (full || t < rows) x = *reinterpret_cast<const double2 *>(mine + t);
+          v[t] = x.x;
+          v[t + 1] = x.y;
+        }
+        double yf, last;
+        if (tab_s) {
+          if (full)
+            yf = chunk_fwd<M, true>(v, ts, M, &last);
+          else
+            yf = chunk_fwd<M, false>(v, ts, rows, &last);
+        } else {
+          if (full)
+            yf = chunk_fwd<M, true>(v, tg, M, &last);
+          else
+            yf = chunk_fwd<M, false>(v, tg, rows, &last);
+        }
         Y[(2 * p2) * R + r2] = yf;
         Y[(2 * p2 + 1) * R + r2] = last;
       }
       HS2_MARK(2);
       __syncthreads();
-      const double E = chunk_interface(ge, Y, P, R, r2, pc, band);
-      if (p2 < P) Es[p2 * R + r2] = E;
+      double E = 0.0;
+      if (solver) {
+        E = chunk_interface(ge, Y, P, R, r2, pc, band);
+        Es[p2 * R + r2] = E;
+      }
       HS2_MARK(3);
       __syncthreads();
-      const double alpha = (p2 > 0 && p2 < P) ? Es[(p2 - 1) * R + r2] : 0.0;
-      if (tab_s) {
-        if (full)
-          chunk_bwd<M, true>(v, ts, M, alpha, E);
-        else
-          chunk_bwd<M, false>(v, ts, rows, alpha, E);
-      } else {
-        if (full)
-          chunk_bwd<M, true>(v, tg, M, alpha, E);
-        else
-          chunk_bwd<M, false>(v, tg, rows, alpha, E);
-      }
-      if (p2 < P) {
+      if (solver) {
+        const double alpha = p2 > 0 ? Es[(p2 - 1) * R + r2] : 0.0;
+        if (tab_s) {
+          if (full)
+            chunk_bwd<M, true>(v, ts, M, alpha, E);
+          else
+            chunk_bwd<M, false>(v, ts, rows, alpha, E);
+        } else {
+          if (full)
+            chunk_bwd<M, true>(v, tg, M, alpha, E);
+          else
+            chunk_bwd<M, false>(v, tg, rows, alpha, E);
+        }
 #pragma unroll
         for (int t = 0; t < M; t += 2)
           if (full || t < rows) *reinterpret_cast<double2 *>(mine + t) = make_double2(v[t], v[t + 1]);
@@ -356,29 +361,27 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
       __syncthreads();
 
       // ------------------------------------------------ phase 3: d1 = w - 2T
+      if (stencil) {
+        const double *cc = Cn + so;
+        const double *bcol = buf + bo;
+        double *Wk = Wout + kbase + (int64_t)j0 * nx + ic;
+        double2 t0[RPT], w[RPT];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (cv[c]) {
-          const double *cc = Cn + so[c];
-          const double *bcol = buf + bo[c];
-          double *Wk = Wout + kbase + (int64_t)j0 * nx + ic[c];
-          double2 t0[R], w[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            t0[r] = *reinterpret_cast<const double2 *>(cc + (r + 1) * BX);
-            w[r] = *reinterpret_cast<const double2 *>(bcol + r * g.Sr);
-          }
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            if (r < nrows)
-              *reinterpret_cast<double2 *>(Wk + (int64_t)r * nx) =
-                  make_double2(fma(-2.0, t0[r].x, w[r].x), fma(-2.0, t0[r].y, w[r].y));
+        for (int r = 0; r < RPT; ++r) {
+          t0[r] = *reinterpret_cast<const double2 *>(cc + (r0 + r + 1) * BX);
+          w[r] = *reinterpret_cast<const double2 *>(bcol + (r0 + r) * g.Sr);
         }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+          if (r0 + r < nrows)
+            *reinterpret_cast<double2 *>(Wk + (int64_t)(r0 + r) * nx) =
+                make_double2(fma(-2.0, t0[r].x, w[r].x), fma(-2.0, t0[r].y, w[r].y));
       }
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int r = 0; r < R; ++r) idc[c][r] = idn[c][r];
+      for (int r = 0; r < RPT; ++r) idc[r] = idn[r];
+      // the buffer's slice is the target of the next iteration's copy: order this
+      // thread's shared-memory accesses before the copy engine's writes
+      if (g.buf_alias) fence_proxy_async();
       HS2_MARK(5);
       __syncthreads();   // buf, Y, Es and the oldest slice are rewritten by the next plane
     }
@@ -390,19 +393,27 @@ template <int M>
 bool xm_geometry(const hs2_plan *p, XmGeom *g, size_t *smem_out, int *threads_out, int *coef_in_smem_out) {
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
-  constexpr int R = HS2_XR, RW = R + 2, NC = M >= 32 ? 2 : 1;
+  constexpr int R = HS2_XR, RW = R + 2;
   const int P = ax.n_chunks;
-  const int threads = R * P;
   const int nx = (int)d.nx, ny = (int)d.ny;
-  if (threads > 256 || 2 * threads * NC < nx || ny < RW) return false;
+  if (R * P > 256 || (nx & 1) || ny < RW) return false;
   if (!ax.d_tab || !ax.d_GE || ax.pitch <= 0) return false;
+  // phases 1 and 3: nx/2 column pairs x RG row groups of RPT rows; as many threads as fit a block
+  const int cpt = nx / 2;
+  if (2 * cpt > 512) return false;
+  g->RPT = 4 * cpt <= 512 ? 2 : 4;
+  int threads = (R / g->RPT) * cpt;
+  if (threads < R * P) threads = R * P;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > 512) return false;
   g->BX = nx <= 256 ? nx : 256;
   g->NXB = (nx + g->BX - 1) / g->BX;
   g->box_stride = ((RW * g->BX + 15) / 16) * 16;
   g->slot_stride = g->NXB * g->box_stride;
   g->Sr = xm_row_pitch(P, M);
+  g->buf_alias = R * g->Sr <= g->slot_stride ? 1 : 0;
   const int coef_in_smem = d.n_classes <= 256 ? 1 : 0;
-  const size_t base = ((size_t)XM_SLOTS * g->slot_stride + (size_t)R * g->Sr + 3 * (size_t)P * R +
+  const size_t base = ((size_t)XM_SLOTS * g->slot_stride + (g->buf_alias ? 0 : (size_t)R * g->Sr) + 3 * (size_t)P * R +
                        (coef_in_smem ? (size_t)d.n_classes * HS2_COEF_STRIDE : 0)) * sizeof(double) +
                       XM_SLOTS * sizeof(uint64_t);
   const size_t tabs = (size_t)HS2_T_PLANES * P * (M + XM_TP) * sizeof(double);
@@ -417,21 +428,19 @@ bool xm_geometry(const hs2_plan *p, XmGeom *g, size_t *smem_out, int *threads_ou
   return true;
 }
 
-template <int M, typename CID>
-int launch_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *done) {
+template <int M, int RPT, typename CID>
+int launch_xm_k(hs2_plan *p, const XmGeom &g0, size_t smem, int threads, int coef_in_smem, const double *T, double *W,
+                cudaStream_t st, bool *done) {
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
   constexpr int R = HS2_XR, RW = R + 2;
   const int P = ax.n_chunks;
   const int nx = (int)d.nx, ny = (int)d.ny, nz = (int)d.nz;
-  XmGeom g;
-  size_t smem = 0;
-  int threads = 0, coef_in_smem = 0;
-  if (!xm_geometry<M>(p, &g, &smem, &threads, &coef_in_smem)) return HS2_OK;
+  XmGeom g = g0;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!hs2_encode_tmap_f64_3d(&tmap, T, (uint64_t)nx, (uint64_t)ny, (uint64_t)nz, (uint32_t)g.BX, RW, 1)) return HS2_OK;
-  auto kern = sweep_xm_kernel<M, CID>;
+  auto kern = sweep_xm_kernel<M, RPT, CID>;
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int occ = 0;
@@ -454,6 +463,16 @@ int launch_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *do
   HS2_CUDA_CHECK(cudaGetLastError());
   *done = true;
   return HS2_OK;
+}
+
+template <int M, typename CID>
+int launch_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *done) {
+  XmGeom g;
+  size_t smem = 0;
+  int threads = 0, coef_in_smem = 0;
+  if (!xm_geometry<M>(p, &g, &smem, &threads, &coef_in_smem)) return HS2_OK;
+  if (g.RPT == 2) return launch_xm_k<M, 2, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
+  return launch_xm_k<M, 4, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
 }
 
 template <typename CID>

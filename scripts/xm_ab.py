@@ -54,7 +54,7 @@ def main():
             plan.ensure_device(dev)
             work = plan._buf("work")
             st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            krs = ("32",) if name == "fold" else ("32", "16", "64", "128")
+            krs = ("32",) if name == "fold" else ("32", "16", "48")
             for kr in krs:
                 os.environ["HS2_XM_KR"] = kr
                 try:

@@ -41,9 +41,11 @@ def test_geometry_limits():
     # slices of 10 rows: shorter grids, odd nx and lines needing more than 256 threads fall back
     assert xm_sim.geometry(8, 9, 32, 8, 4, 32) is None
     assert xm_sim.geometry(8, 16, 31, 8, 4, 32) is None
-    assert xm_sim.geometry(8, 16, 2048, 32, 64, 32) is None
+    assert xm_sim.geometry(8, 16, 1024, 32, 32, 32) is None
     g = xm_sim.geometry(512, 512, 512, 32, 16, 32)
-    assert g["threads"] == 128 and g["NXB"] == 2 and g["n_items"] == 1024
-    # bytes of the four slices + solve buffer at 512^3 stay inside 227 KB with the tables
-    smem = (4 * g["slot_stride"] + 8 * g["Sr"] + 3 * 16 * 8 + 27 * 8 + 5 * 16 * 34 + 16 * 34) * 8 + 32
+    assert g["threads"] == 512 and g["RPT"] == 4 and g["NXB"] == 2 and g["n_items"] == 1024 and g["buf_alias"]
+    # bytes of the four slices (the solve buffer lives in one of them) + tables at 512^3 stay inside 227 KB
+    smem = (4 * g["slot_stride"] + 3 * 16 * 8 + 27 * 8 + 5 * 16 * 34 + 16 * 34) * 8 + 32
     assert smem <= 232448
+    assert xm_sim.geometry(64, 64, 256, 16, 16, 32)["RPT"] == 2
+    assert not xm_sim.geometry(12, 20, 64, 8, 8, 32)["buf_alias"]      # M=8: padded rows outgrow a slice

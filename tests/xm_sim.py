@@ -20,16 +20,23 @@ def row_pitch(P, M):
 
 
 def geometry(nz, ny, nx, M, P, KR):
-    threads = R * P
-    NC = 2 if M >= 32 else 1
-    if threads > 256 or 2 * threads * NC < nx or ny < RW or nx % 2:
+    if R * P > 256 or nx % 2 or ny < RW:
         return None
-    g = dict(threads=threads, NC=NC)
+    cpt = nx // 2
+    if 2 * cpt > 512:
+        return None
+    RPT = 2 if 4 * cpt <= 512 else 4
+    threads = max((R // RPT) * cpt, R * P)
+    threads = -(-threads // 32) * 32
+    if threads > 512:
+        return None
+    g = dict(threads=threads, RPT=RPT, solvers=R * P)
     g["BX"] = nx if nx <= 256 else 256
     g["NXB"] = -(-nx // g["BX"])
     g["box_stride"] = -(-(RW * g["BX"]) // 16) * 16
     g["slot_stride"] = g["NXB"] * g["box_stride"]
     g["Sr"] = row_pitch(P, M)
+    g["buf_alias"] = R * g["Sr"] <= g["slot_stride"]
     g["KR"] = max(1, min(KR, nz))
     g["tiles_y"] = -(-ny // R)
     g["n_items"] = -(-nz // g["KR"]) * g["tiles_y"]
@@ -43,7 +50,8 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
     g = geometry(nz, ny, nx, M, P, KR)
     assert g is not None, "grid outside the kernel's range"
     BX, NXB, box_stride, slot_stride, Sr = g["BX"], g["NXB"], g["box_stride"], g["slot_stride"], g["Sr"]
-    nthreads, NC = g["threads"], g["NC"]
+    nthreads, RPT, nsolvers, alias = g["threads"], g["RPT"], g["solvers"], g["buf_alias"]
+    RG, cpt = R // RPT, nx // 2
     tab_u, GE_u = plan.chunk_tabs[0]          # [nu, 5, pitch], [nu, P, 2P]
     pitch = tab_u.shape[2]
     line_id = plan.line_id[0].cpu().numpy()   # x-lines k*ny + j
@@ -58,7 +66,7 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
         completed = [0] * SLOTS
         waited = [0] * SLOTS
         phase_bits = 0
-        buf = np.full(R * Sr, np.nan)
+        buf_own = np.full(R * Sr, np.nan)
         Y = np.zeros(2 * P * R)
         Es = np.zeros(P * R)
         # shared-memory tables of the block's first line
@@ -117,10 +125,6 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
             for q in range(3):
                 if needed(q):
                     issue(q)
-            rq = []
-            for q in range(RW):
-                j = min(max(j0 + q - 1, 0), ny - 1)
-                rq.append((j - (j0 - 1)) * BX)
             for it in range(n_it):
                 k = ka + it
                 if needed(it + 3):
@@ -136,35 +140,53 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
                 sH = ((it + 2) & (SLOTS - 1)) if k + 1 < nz else sC
                 assert tag[sC] == (k, j0) and tag[sL] == (max(k - 1, 0), j0) and tag[sH] == (min(k + 1, nz - 1), j0)
                 Cn, Lo, Hi = sC * slot_stride, sL * slot_stride, sH * slot_stride
-                # ---------------- phase 1
+                # solve buffer: own region, or the slice of plane k-1 (slot it & 3)
+                if alias:
+                    bs = it & (SLOTS - 1)
+                    assert completed[bs] == waited[bs], "solve buffer placed in a slice with a copy in flight"
+                    buf, boff = slots, bs * slot_stride
+                else:
+                    buf, boff = buf_own, 0
+                # ---------------- phase 1: all reads, barrier, then the stores
+                outv = {}
                 for tid in range(nthreads):
-                    for c in range(NC):
-                        i = 2 * tid + 2 * nthreads * c
-                        if i >= nx:
-                            continue
-                        xb = i // BX
-                        so = xb * box_stride + (i - xb * BX)
-                        bo = i + PAD * (i // M)
-                        for r in range(R):
-                            jj = min(j0 + r, ny - 1)
-                            for e in range(2):
-                                cf = coef[cid[k, jj, i + e]]
-                                tt = slots[Cn + so + rq[r + 1] + e]
-                                vym = slots[Cn + so + rq[r] + e]
-                                vyp = slots[Cn + so + rq[r + 2] + e]
-                                vzm = slots[Lo + so + (r + 1) * BX + e]
-                                vzp = slots[Hi + so + (r + 1) * BX + e]
-                                rr = cf[2] * (vym - tt) + cf[3] * (vyp - tt) + cf[4] * (vzm - tt) + cf[5] * (vzp - tt)
-                                buf[bo + r * Sr + e] = 2.0 * tt + rr
+                    rg = tid // cpt
+                    if rg >= RG:
+                        continue
+                    i = 2 * (tid - rg * cpt)
+                    r0 = rg * RPT
+                    so = (i // BX) * box_stride + (i % BX)
+                    rq = []
+                    for q in range(RPT + 2):
+                        j = min(max(j0 + r0 + q - 1, 0), ny - 1)
+                        rq.append((j - (j0 - 1)) * BX)
+                    for r in range(RPT):
+                        jj = min(j0 + r0 + r, ny - 1)
+                        for e in range(2):
+                            cf = coef[cid[k, jj, i + e]]
+                            tt = slots[Cn + so + rq[r + 1] + e]
+                            vym = slots[Cn + so + rq[r] + e]
+                            vyp = slots[Cn + so + rq[r + 2] + e]
+                            vzm = slots[Lo + so + (r0 + r + 1) * BX + e]
+                            vzp = slots[Hi + so + (r0 + r + 1) * BX + e]
+                            rr = cf[2] * (vym - tt) + cf[3] * (vyp - tt) + cf[4] * (vzm - tt) + cf[5] * (vzp - tt)
+                            outv[(tid, r, e)] = 2.0 * tt + rr
+                if alias:
+                    tag[bs] = None                        # the slice of plane k-1 is gone from here on
+                for (tid, r, e), val in outv.items():
+                    rg = tid // cpt
+                    i = 2 * (tid - rg * cpt)
+                    bo = i + PAD * (i // M)
+                    buf[boff + bo + (rg * RPT + r) * Sr + e] = val
                 # ---------------- phase 2 (forward)
                 v_all = {}
-                for tid in range(nthreads):
+                for tid in range(nsolvers):
                     r2, p2 = tid % R, tid // R
-                    pc = p2 if p2 < P else P - 1
+                    pc = p2
                     c0 = pc * M
                     rows = min(M, nx - c0)
                     lid = line_id[k * ny + j0 + (r2 if r2 < nrows else 0)]
-                    mine = r2 * Sr + pc * (M + PAD)
+                    mine = boff + r2 * Sr + pc * (M + PAD)
                     tab_s = lid == lid_c
 
                     def tb(pl, t, tab_s=tab_s, pc=pc, c0=c0, lid=lid):
@@ -177,12 +199,11 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
                         prev = v[t] * tb(T_INV, t) - tb(T_F, t) * prev
                         v[t] = prev
                         yf += tb(T_C, t) * prev
-                    if p2 < P:
-                        Y[(2 * p2) * R + r2] = yf
-                        Y[(2 * p2 + 1) * R + r2] = prev
+                    Y[(2 * p2) * R + r2] = yf
+                    Y[(2 * p2 + 1) * R + r2] = prev
                     v_all[tid] = (v, tb, rows, lid, tab_s, pc, r2, p2, mine)
                 E_all = {}
-                for tid in range(nthreads):
+                for tid in range(nsolvers):
                     v, tb, rows, lid, tab_s, pc, r2, p2, mine = v_all[tid]
                     E = 0.0
                     for q in range(max(0, pc - band), min(P - 1, pc + band) + 1):
@@ -192,35 +213,35 @@ def sweep_x(plan, T, KR=32, n_blocks=3):
                             g0, g1 = GE_u[lid, pc, 2 * q], GE_u[lid, pc, 2 * q + 1]
                         E += g0 * Y[(2 * q) * R + r2] + g1 * Y[(2 * q + 1) * R + r2]
                     E_all[tid] = E
-                    if p2 < P:
-                        Es[p2 * R + r2] = E
-                for tid in range(nthreads):
+                    Es[p2 * R + r2] = E
+                for tid in range(nsolvers):
                     v, tb, rows, lid, tab_s, pc, r2, p2, mine = v_all[tid]
                     E = E_all[tid]
-                    alpha = Es[(p2 - 1) * R + r2] if 0 < p2 < P else 0.0
+                    alpha = Es[(p2 - 1) * R + r2] if p2 > 0 else 0.0
                     nxt = E
                     for t in range(rows - 1, -1, -1):
                         if t < rows - 1:
                             nxt = (v[t] - alpha * tb(T_S, t)) - tb(T_CP, t) * nxt
                         v[t] = nxt
-                    if p2 < P:
-                        for t in range(rows):
-                            buf[mine + t] = v[t]
+                    for t in range(rows):
+                        buf[mine + t] = v[t]
                 # ---------------- phase 3
                 for tid in range(nthreads):
-                    for c in range(NC):
-                        i = 2 * tid + 2 * nthreads * c
-                        if i >= nx:
+                    rg = tid // cpt
+                    if rg >= RG:
+                        continue
+                    i = 2 * (tid - rg * cpt)
+                    r0 = rg * RPT
+                    so = (i // BX) * box_stride + (i % BX)
+                    bo = i + PAD * (i // M)
+                    for r in range(RPT):
+                        if r0 + r >= nrows:
                             continue
-                        xb = i // BX
-                        so = xb * box_stride + (i - xb * BX)
-                        bo = i + PAD * (i // M)
-                        for r in range(nrows):
-                            for e in range(2):
-                                t0 = slots[Cn + so + (r + 1) * BX + e]
-                                w = buf[bo + r * Sr + e]
-                                assert np.isnan(W[k, j0 + r, i + e]), "cell written twice"
-                                W[k, j0 + r, i + e] = w - 2.0 * t0
+                        for e in range(2):
+                            t0 = slots[Cn + so + (r0 + r + 1) * BX + e]
+                            w = buf[boff + bo + (r0 + r) * Sr + e]
+                            assert np.isnan(W[k, j0 + r0 + r, i + e]), "cell written twice"
+                            W[k, j0 + r0 + r, i + e] = w - 2.0 * t0
             assert completed == waited, "copies left unconsumed at the end of an item"
     assert not np.isnan(W).any(), "cells never written"
     return W
