@@ -53,6 +53,7 @@ struct XmGeom {
   int Sr;           // row pitch of the solve buffer
   int tab_in_smem;  // factor tables of the block's line class in shared memory
   int ge_in_smem;   // ... and its interface-operator rows
+  int R;            // x-lines per tile (8 or 4)
   int buf_alias;    // solve buffer lives in the slice of plane k-1
   int RPT;          // rows per thread in phases 1 and 3 (2 or 4)
   int KR;           // planes per work item
@@ -83,13 +84,12 @@ __device__ __forceinline__ void xm_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
-template <int M, int RPT, typename CID>
+template <int M, int RPT, int R, typename CID>
 __global__ void __launch_bounds__(512, 1)
 sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ Wout, const CID *__restrict__ cid,
                 const double *__restrict__ coef_g, int n_classes, int coef_in_smem,
                 const uint32_t *__restrict__ line_id, const double *__restrict__ tab, int pitch,
                 const double *__restrict__ GE, int nz, int ny, int nx, int P, int band, XmGeom g) {
-  constexpr int R = HS2_XR;
   constexpr int RW = R + 2;
   constexpr int RG = R / RPT;           // row groups of phases 1 and 3
   extern __shared__ __align__(128) unsigned char xm_raw[];
@@ -393,7 +393,14 @@ template <int M>
 bool xm_geometry(const hs2_plan *p, XmGeom *g, size_t *smem_out, int *threads_out, int *coef_in_smem_out) {
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
-  constexpr int R = HS2_XR, RW = R + 2;
+  // HS2_XM_R: x-lines per tile, 8 (one 512-thread block per SM at nx = 512) or 4 (two 256-thread
+  // blocks per SM, factor tables from global memory / L1); HS2_XM_TAB=0/1 overrides where the tables live
+  const char *r_env = getenv("HS2_XM_R");
+  const int R = (r_env && atoi(r_env) == 4) ? 4 : 8;
+  const int RW = R + 2;
+  const char *t_env = getenv("HS2_XM_TAB");
+  const bool want_tab = t_env ? atoi(t_env) != 0 : R == 8;
+  g->R = R;
   const int P = ax.n_chunks;
   const int nx = (int)d.nx, ny = (int)d.ny;
   if (R * P > 256 || (nx & 1) || ny < RW) return false;
@@ -418,7 +425,7 @@ bool xm_geometry(const hs2_plan *p, XmGeom *g, size_t *smem_out, int *threads_ou
                       XM_SLOTS * sizeof(uint64_t);
   const size_t tabs = (size_t)HS2_T_PLANES * P * (M + XM_TP) * sizeof(double);
   const size_t ges = (size_t)P * (2 * P + 2) * sizeof(double);
-  g->tab_in_smem = base + tabs <= (size_t)p->max_smem_optin ? 1 : 0;
+  g->tab_in_smem = (want_tab && base + tabs <= (size_t)p->max_smem_optin) ? 1 : 0;
   g->ge_in_smem = (g->tab_in_smem && base + tabs + ges <= (size_t)p->max_smem_optin) ? 1 : 0;
   const size_t smem = base + (g->tab_in_smem ? tabs : 0) + (g->ge_in_smem ? ges : 0);
   if (smem > (size_t)p->max_smem_optin) return false;
@@ -428,19 +435,19 @@ bool xm_geometry(const hs2_plan *p, XmGeom *g, size_t *smem_out, int *threads_ou
   return true;
 }
 
-template <int M, int RPT, typename CID>
+template <int M, int RPT, int R, typename CID>
 int launch_xm_k(hs2_plan *p, const XmGeom &g0, size_t smem, int threads, int coef_in_smem, const double *T, double *W,
                 cudaStream_t st, bool *done) {
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
-  constexpr int R = HS2_XR, RW = R + 2;
+  constexpr int RW = R + 2;
   const int P = ax.n_chunks;
   const int nx = (int)d.nx, ny = (int)d.ny, nz = (int)d.nz;
   XmGeom g = g0;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!hs2_encode_tmap_f64_3d(&tmap, T, (uint64_t)nx, (uint64_t)ny, (uint64_t)nz, (uint32_t)g.BX, RW, 1)) return HS2_OK;
-  auto kern = sweep_xm_kernel<M, RPT, CID>;
+  auto kern = sweep_xm_kernel<M, RPT, R, CID>;
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int occ = 0;
@@ -471,8 +478,12 @@ int launch_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *do
   size_t smem = 0;
   int threads = 0, coef_in_smem = 0;
   if (!xm_geometry<M>(p, &g, &smem, &threads, &coef_in_smem)) return HS2_OK;
-  if (g.RPT == 2) return launch_xm_k<M, 2, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
-  return launch_xm_k<M, 4, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
+  if (g.R == 4) {
+    if (g.RPT == 2) return launch_xm_k<M, 2, 4, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
+    return launch_xm_k<M, 4, 4, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
+  }
+  if (g.RPT == 2) return launch_xm_k<M, 2, 8, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
+  return launch_xm_k<M, 4, 8, CID>(p, g, smem, threads, coef_in_smem, T, W, st, done);
 }
 
 template <typename CID>

@@ -51,8 +51,10 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,kwargs,chunk_x,kr", CASES)
-def test_march_equals_fold(hs, name, kwargs, chunk_x, kr, monkeypatch):
+@pytest.mark.parametrize("R", ["8", "4"])
+def test_march_equals_fold(hs, name, kwargs, chunk_x, kr, R, monkeypatch):
     import torch
+    monkeypatch.setenv("HS2_XM_R", R)                   # x-lines per tile
     if chunk_x:
         monkeypatch.setenv("HS2_CHUNK_X", chunk_x)
     if kr:
@@ -76,9 +78,11 @@ def test_march_equals_fold(hs, name, kwargs, chunk_x, kr, monkeypatch):
     ("uniform_slab", dict(shape=(33, 34, 50)), 6),
     ("sources_demo", dict(nz=12, ny=10, nx=14), None),     # steps with sources go through kernels_xf.cu, the others march
 ])
-def test_march_steps_match_oracle(hs, name, kwargs, nsteps, monkeypatch):
+@pytest.mark.parametrize("R", ["8", "4"])
+def test_march_steps_match_oracle(hs, name, kwargs, nsteps, R, monkeypatch):
     import adi_oracle
     monkeypatch.setenv("HS2_X_KERNEL", "march")
+    monkeypatch.setenv("HS2_XM_R", R)
     prob = problems.ALL[name](hs, **kwargs)
     n = prob["nsteps"] if nsteps is None else nsteps
     got = util.run_b200(hs, prob, nsteps=n)

@@ -28,12 +28,13 @@ def _plan(name, kwargs, chunk_x=None, monkeypatch=None):
     ("steelonwater", dict(nz=6, ny=20, nx=24), 3, 8),             # FIXED cells, thin layer
     ("composite", dict(nz=8, ny=16, nx=32, ply=4), 5, 16),
 ])
-def test_march_kernel_transcription_equals_plain_sweep(name, kwargs, KR, chunk_x, monkeypatch):
+@pytest.mark.parametrize("R", [8, 4])
+def test_march_kernel_transcription_equals_plain_sweep(name, kwargs, KR, chunk_x, R, monkeypatch):
     plan = _plan(name, kwargs, chunk_x, monkeypatch)
     rng = np.random.default_rng(3)
     T = rng.random(plan.shape)
     want = emul.solve_axis(plan, emul.rhs(plan, T, None, None, None), 0)
-    got = xm_sim.sweep_x(plan, T, KR=KR, n_blocks=3)
+    got = xm_sim.sweep_x(plan, T, KR=KR, n_blocks=3, R=R)
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
 
 

@@ -9,7 +9,7 @@ import numpy as np
 
 from heatsim2_b200.plan import T_INV, T_F, T_C, T_S, T_CP
 
-R, RW, SLOTS, PAD, TP = 8, 10, 4, 2, 2
+SLOTS, PAD, TP = 4, 2, 2
 
 
 def row_pitch(P, M):
@@ -19,7 +19,8 @@ def row_pitch(P, M):
     return s
 
 
-def geometry(nz, ny, nx, M, P, KR):
+def geometry(nz, ny, nx, M, P, KR, R=8):
+    RW = R + 2
     if R * P > 256 or nx % 2 or ny < RW:
         return None
     cpt = nx // 2
@@ -30,7 +31,7 @@ def geometry(nz, ny, nx, M, P, KR):
     threads = -(-threads // 32) * 32
     if threads > 512:
         return None
-    g = dict(threads=threads, RPT=RPT, solvers=R * P)
+    g = dict(threads=threads, RPT=RPT, solvers=R * P, R=R)
     g["BX"] = nx if nx <= 256 else 256
     g["NXB"] = -(-nx // g["BX"])
     g["box_stride"] = -(-(RW * g["BX"]) // 16) * 16
@@ -43,11 +44,12 @@ def geometry(nz, ny, nx, M, P, KR):
     return g
 
 
-def sweep_x(plan, T, KR=32, n_blocks=3):
+def sweep_x(plan, T, KR=32, n_blocks=3, R=8):
     """d1 of stage 0 for the whole grid, computed the way sweep_xm_kernel does."""
+    RW = R + 2
     nz, ny, nx = plan.shape
     M, P = plan.chunk[0]
-    g = geometry(nz, ny, nx, M, P, KR)
+    g = geometry(nz, ny, nx, M, P, KR, R)
     assert g is not None, "grid outside the kernel's range"
     BX, NXB, box_stride, slot_stride, Sr = g["BX"], g["NXB"], g["box_stride"], g["slot_stride"], g["Sr"]
     nthreads, RPT, nsolvers, alias = g["threads"], g["RPT"], g["solvers"], g["buf_alias"]
