@@ -148,9 +148,11 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
   const int rows = min(M, nx - c0);
   const bool full = rows == M;
   const int mine_off = r2 * g.Sr + pc * (M + XM_PAD);
+  // TabShared::ld is a non-volatile asm the compiler may hoist above the `tab_s` test, so the
+  // address must be readable even when the block keeps no tables (found with compute-sanitizer)
   TabShared ts;
-  ts.a = smem_u32(s_tab + pc * (M + XM_TP));
-  ts.pitch_b = (uint32_t)(P * (M + XM_TP)) * 8u;
+  ts.a = g.tab_in_smem ? smem_u32(s_tab + pc * (M + XM_TP)) : smem_u32(slots);
+  ts.pitch_b = g.tab_in_smem ? (uint32_t)(P * (M + XM_TP)) * 8u : 0u;
 
   // phase-1/3 role (threads 0 .. RG*nx/2-1): column pair ic, ic+1 of rows r0 .. r0+RPT-1
   const int cpt = nx >> 1;

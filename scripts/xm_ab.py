@@ -90,7 +90,8 @@ def main():
         best = min(ok, key=lambda r: r["step_ms"])
         out["best_march"] = best
         out["best_fold"] = min(folds, key=lambda r: r["step_ms"]) if folds else None
-        with open(os.path.join(ROOT, "gpurun_out", "xm_best.env"), "w") as f:
+        if out["best_fold"] is None or best["step_ms"] < out["best_fold"]["step_ms"]:
+          with open(os.path.join(ROOT, "gpurun_out", "xm_best.env"), "w") as f:
             f.write("export HS2_X_KERNEL=march HS2_CHUNK_X=%d %s\n" % (best["chunk_x"], " ".join("%s=%s" % kv for kv in best["env"].items())))
         print("best march:", json.dumps(best))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
