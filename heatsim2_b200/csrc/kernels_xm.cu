@@ -61,6 +61,21 @@ struct XmGeom {
   int n_items;
 };
 
+// Shared-memory table accessor of this kernel: chunk_core.cuh's TabShared with a VOLATILE load.
+// The block may keep no tables at all (tab_in_smem = 0); a plain asm is a pure function to the
+// compiler, which then turns ld(select(c, tables, elsewhere)) into select(c, ld(tables), ld(elsewhere))
+// and reads past the end of shared memory (found with compute-sanitizer; SASS: LDS.64 ahead of the SEL).
+struct XmTabShared {
+  uint32_t a;        // shared-window byte address of plane 0 at this thread's first row
+  uint32_t pitch_b;  // bytes between planes
+  __device__ __forceinline__ uint32_t plane(int pl) const { return a + pl * pitch_b; }
+  __device__ __forceinline__ static double ld(uint32_t q, int t) {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(q + 8u * (uint32_t)t));
+    return x;
+  }
+};
+
 __device__ __forceinline__ bool xm_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -148,9 +163,7 @@ sweep_xm_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ W
   const int rows = min(M, nx - c0);
   const bool full = rows == M;
   const int mine_off = r2 * g.Sr + pc * (M + XM_PAD);
-  // TabShared::ld is a non-volatile asm the compiler may hoist above the `tab_s` test, so the
-  // address must be readable even when the block keeps no tables (found with compute-sanitizer)
-  TabShared ts;
+  XmTabShared ts;
   ts.a = g.tab_in_smem ? smem_u32(s_tab + pc * (M + XM_TP)) : smem_u32(slots);
   ts.pitch_b = g.tab_in_smem ? (uint32_t)(P * (M + XM_TP)) * 8u : 0u;
 

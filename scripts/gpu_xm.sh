@@ -15,8 +15,8 @@ test -f gpurun_out/xm_best.env || exit 0
 cat gpurun_out/xm_best.env
 timeout 240 python bench.py --no-cpu-baseline > gpurun_out/bench_march_$TAG.json 2> gpurun_out/bench_march_$TAG.err
 python scripts/bench_line.py "bench march" < gpurun_out/bench_march_$TAG.json
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"sweep_xm" -s 2 -c 1 -o gpurun_out/prof_xm_$TAG -f python profiles/run_steps.py 512 4 > gpurun_out/prof_xm_$TAG.log 2>&1
-tail -2 gpurun_out/prof_xm_$TAG.log
 timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/suite_march_$TAG.log 2>&1
 echo "suite(march) rc=$?"
 tail -5 gpurun_out/suite_march_$TAG.log
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"sweep_xm" -s 2 -c 1 -o gpurun_out/prof_xm_$TAG -f python profiles/run_steps.py 512 4 > gpurun_out/prof_xm_$TAG.log 2>&1
+tail -2 gpurun_out/prof_xm_$TAG.log

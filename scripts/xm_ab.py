@@ -47,9 +47,7 @@ def main():
     variants = [("fold", {}),
                 ("march", {"HS2_XM_R": "8", "HS2_XM_KR": "32"}),
                 ("march", {"HS2_XM_R": "4", "HS2_XM_KR": "32"}),
-                ("march", {"HS2_XM_R": "4", "HS2_XM_KR": "16"}),
-                ("march", {"HS2_XM_R": "4", "HS2_XM_KR": "32", "HS2_XM_TAB": "1"}),
-                ("march", {"HS2_XM_R": "8", "HS2_XM_KR": "32", "HS2_XM_TAB": "0"})]
+                ("march", {"HS2_XM_R": "4", "HS2_XM_KR": "16"})]
     for chunk in ("32", "16"):
         os.environ["HS2_CHUNK_X"] = chunk
         prob = problems.uniform_slab(hs, shape=(grid, grid, grid), random_T0=False)
