@@ -1,34 +1,44 @@
 // kernels_xm.cu - stage 0 of the ADI step, z-marching variant of the folded
-// x-sweep of kernels_xf.cu (same arithmetic, same results bit for bit on full
-// chunks): the input field never passes through registers or L1 on its way in.
+// x-sweep of kernels_xf.cu (same arithmetic, bit-identical results): the input
+// field never passes through registers or L1 on its way in.  OPT-IN
+// (HS2_FLAG_X_MARCH / HS2_X_KERNEL=march): measured on B200 it is 10 % slower
+// than kernels_xf.cu at 512^3 (0.90 vs 0.82 ms) - it keeps one tile per SM where
+// the folded kernel keeps four, and the number of solve chains in flight is what
+// bounds the sweep (profiles/NOTES_r01.md, third part).
 //
 //   d1 = A^-1 [ 2 T + q ] - 2 T ,  q = M^-1 (Ly + Lz) T ,  A = I - 1/2 M^-1 Lx
 //   (replaces B0.dot(T) + tridiagsolve of stage 0,
 //    heatsim2/alternatingdirection_c_pyx.pyx:397-412)
 //
-// A persistent block owns work items (tile of R = 8 x-lines j0..j0+7, range of
+// A persistent block owns work items (tile of R x-lines j0..j0+R-1, range of KR
 // planes [ka, kb)) and marches through the planes of an item.  The rows
-// j0-1..j0+8 of every plane are fetched ONCE by the tensor copy engine
+// j0-1..j0+R of every plane are fetched ONCE by the tensor copy engine
 // (cp.async.bulk.tensor, completion on an mbarrier) into a ring of four
 // shared-memory slices: while plane k is worked on, slices k-1, k, k+1 are
-// resident (z neighbours and y halo come out of shared memory) and plane k+2,
-// k+3 are in flight - two planes (2 x 40 KB at nx = 512) of loads per SM are
-// outstanding at any time without holding a single register.  The L2 -> SM
+// resident (z neighbours and y halo come out of shared memory) and planes k+2,
+// k+3 are in flight - two planes (2 x 40 KB at nx = 512, R = 8) of loads per SM
+// are outstanding at any time without holding a single register.  The L2 -> SM
 // traffic per cell falls from 37 B (kernels_xf.cu: z neighbours and the phase-3
-// re-read come from L2 through L1) to 10 B, and phase 3 reads T from the slice
-// instead of re-reading it.
+// re-read come from L2 through L1) to 13-18 B, and phase 3 reads T from the slice.
 //
-//  phase 1  threads own column pairs; 5-point stencil from the three slices,
-//           2T + q to the chunk-padded solve buffer (16-byte accesses);
-//  phase 2  thread (line r, chunk p) runs the partitioned solve in registers
-//           (chunk_core.cuh); factor tables and interface-operator rows of the
-//           block's line class sit in shared memory (8-byte broadcast loads),
-//           other classes read the global tables;
+//  phase 1  nx/2 column pairs x R/RPT row groups of threads (up to 512); 5-point
+//           stencil from the three slices into registers, then - after a barrier,
+//           because the solve buffer aliases the slice of plane k-1 - 2T + q to
+//           the chunk-padded solve buffer (16-byte accesses);
+//  phase 2  the first R*P threads: thread (line r, chunk p) runs the partitioned
+//           solve in registers (chunk_core.cuh); factor tables and interface-
+//           operator rows of the block's line class sit in shared memory (8-byte
+//           broadcast loads), other classes read the global tables;
 //  phase 3  d1 = w - 2T, T from the centre slice, coalesced 16-byte stores.
+//
+// R = 8 (default; one 512-thread block per SM at nx = 512) or 4 (HS2_XM_R=4: two
+// 256-thread blocks per SM, tables from global memory).  The indexing and the
+// copy/wait protocol are transcribed thread by thread in tests/xm_sim.py and
+// checked on the CPU (tests/test_xmarch_sim.py).
 //
 // Not handled here (the caller falls back to kernels_xf.cu): steps with an
 // active volumetric source, slab halos / plane parts of the multi-GPU path,
-// grids whose slices do not fit shared memory.
+// nx > 512, fewer than R+2 rows, grids whose slices do not fit shared memory.
 #include "x_common.cuh"
 #include "tma_util.cuh"
 #include <stdlib.h>
