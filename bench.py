@@ -52,15 +52,23 @@ class ClockSampler(object):
         self.lines = []
         self.proc = None
 
-    def start(self):
+    CMD = ["nvidia-smi"]
+
+    def start(self, wait_s=5.0):
+        """Start sampling every 20 ms and return once the first sample has arrived (nvidia-smi can
+        take longer to start than a short timed region lasts), or after ``wait_s`` seconds."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(self.CMD + ["-i", str(self.index), "--query-gpu=" + self.Q,
+                                                     "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < wait_s and self.proc.poll() is None:
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
