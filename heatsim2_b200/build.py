@@ -12,6 +12,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhs2b200.so")
+OBJ = os.path.join(PKG, "_obj")          # object files (git-ignored, not sent to the GPU box)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
          "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
@@ -32,12 +33,26 @@ def _stale():
 
 
 def build(force=False, verbose=False, extra=()):
+    """Compile every csrc/*.cu to an object file (one nvcc per file, in parallel: the
+    files share no device code) and link them into libhs2b200.so."""
     if not force and not _stale():
         return LIB
-    cmd = [NVCC] + FLAGS + list(extra) + sources() + ["-o", LIB]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ, exist_ok=True)
+    compile_flags = [f for f in FLAGS if f != "-shared"]
+    jobs = []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        jobs.append((obj, [NVCC] + compile_flags + list(extra) + ["-c", src, "-o", obj]))
     if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+        for _, cmd in jobs:
+            print(" ".join(cmd))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda j: subprocess.check_call(j[1]), jobs))
+    link = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [j[0] for j in jobs] + ["-o", LIB]
+    if verbose:
+        print(" ".join(link))
+    subprocess.check_call(link)
     return LIB
 
 
