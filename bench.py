@@ -34,7 +34,10 @@ UNIT = "cell-updates/s"
 BYTES_PER_CELL = {"x": 16, "y": 16, "z": 24}        # 56 B per cell-update
 
 
-def grid_for(n_gpus, g):
+def grid_for(n_gpus, g, scaling="weak"):
+    if scaling == "strong":
+        # BASELINE configs[4]: the SAME (2g)^3 grid (1024^3) on 1, 2, 4 and 8 GPUs
+        return (2 * g, 2 * g, 2 * g)
     if n_gpus == 1:
         return (g, g, g)
     # weak scaling: g^3 cells per GPU
@@ -191,7 +194,7 @@ def run_reference_arm(args):
         v, el = time_oracle_port(grid, args.steps, args.warmup)
         kind, cores = "port", 1
         sample = "numpy oracle port, %d steps at %d^3" % (args.steps, grid)
-    shape = grid_for(args.gpus, args.grid)
+    shape = grid_for(args.gpus, args.grid, args.scaling)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -217,7 +220,7 @@ def run_b200_single(args):
     _cabi.lib()
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    shape = grid_for(1, args.grid)
+    shape = grid_for(1, args.grid, args.scaling)
     if args.shape:
         shape = tuple(int(v) for v in args.shape.split(","))
     t0 = time.perf_counter()
@@ -331,7 +334,7 @@ def run_b200_single(args):
         e2e_resident = {"error": str(exc)[:200]}
     base = cpu_baseline() if not args.no_cpu_baseline else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(shape), "grid": list(shape), "cells": n,
                        "l2": "inputs larger than L2 (3 arrays of %.2f GB vs 126 MB)" % (n * 8 / 1e9),
@@ -351,13 +354,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", default="", help="nz,ny,nx override of the single-GPU grid (experiments)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: grid^3 cells per GPU (default, the driver's SCALE run); strong: (2*grid)^3 = 1024^3 "
+                         "on every GPU count (BASELINE configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.gpus == 1:
         return run_b200_single(args)
     from heatsim2_b200 import dist_bench
-    return dist_bench.run(args, grid_for(args.gpus, args.grid), workload_name, ClockSampler)
+    return dist_bench.run(args, grid_for(args.gpus, args.grid, args.scaling), workload_name, ClockSampler)
 
 
 if __name__ == "__main__":

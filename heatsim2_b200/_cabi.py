@@ -56,6 +56,8 @@ PROTOTYPES = {
     "hs2_plan_destroy": (ctypes.c_int, [c_void_p]),
     "hs2_plan_launches_per_step": (ctypes.c_int, [c_void_p]),
     "hs2_plan_x_kernel": (ctypes.c_int, [c_void_p]),
+    "hs2_plan_last_kernel": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "hs2_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "hs2_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_x_part": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, ctypes.c_int,

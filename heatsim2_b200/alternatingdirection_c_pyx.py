@@ -305,6 +305,8 @@ def run_adi_steps_n(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, 
                 rec_probe.append(cur[idx])
             if surface_dz is not None:
                 rec_surf.append(st.insulating_z_min_surface_temperature(cur, surface_dz))
+    if hasattr(plan, "check"):
+        plan.check()           # multi-GPU plans: raise if a peer wait ever expired
     record = {"step": rec_steps}
     if idx is not None:
         record["probes"] = torch.stack(rec_probe).cpu().numpy() if rec_probe else np.zeros((0, len(probes)))

@@ -48,6 +48,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
   p->n = desc->nz * desc->ny * desc->nx;
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  p->last_kernel[0] = p->last_kernel[1] = p->last_kernel[2] = HS2_K_NONE;
   *out = p;
   return HS2_OK;
 }
@@ -65,7 +66,18 @@ int hs2_plan_launches_per_step(const hs2_plan *plan) {
 int hs2_plan_x_kernel(const hs2_plan *plan) {
   if (!plan) return -1;
   if (!hs2_tile_xf_supported(plan)) return HS2_XK_WHOLE_LINE;
-  return hs2_tile_xm_supported(plan) ? HS2_XK_MARCH : HS2_XK_FOLD;
+  return HS2_XK_FOLD;
+}
+
+int hs2_plan_last_kernel(const hs2_plan *plan, int axis) {
+  if (!plan || axis < 0 || axis > 2) return -1;
+  return plan->last_kernel[axis];
+}
+
+const char *hs2_kernel_name(int code) {
+  static const char *const names[] = {"none", "whole-line", "tile", "tile-tma", "tile-tma-512", "tile-cpasync",
+                                      "tile-cpasync-512", "x-fold", "z-slab"};
+  return (code >= 0 && code < (int)(sizeof(names) / sizeof(names[0]))) ? names[code] : "?";
 }
 
 int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_source *src, const double *d_halo_lo,

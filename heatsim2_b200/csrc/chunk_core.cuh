@@ -109,7 +109,7 @@ __device__ __forceinline__ void chunk_backward_short(double (&v)[M], const doubl
 // (yf_0, yl_0, yf_1, yl_1, ...) values of this line held in Y[2P][ld] column w.
 // The operator decays geometrically away from the diagonal; `band` (from the
 // host, chunk_factors) is the half-width beyond which every entry is below
-// 1e-18 of the row maximum, so only chunks p-band..p+band are visited.
+// 1e-16 of the row maximum (plan.py interface_band), so only chunks p-band..p+band are visited.
 __device__ __forceinline__ double chunk_interface(const double *__restrict__ ge, const double *Y, int P, int ld, int w,
                                                   int p, int band) {
   double e0 = 0.0, e1 = 0.0;

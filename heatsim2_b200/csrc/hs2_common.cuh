@@ -12,6 +12,7 @@ struct hs2_plan {
   int64_t n;           // nz*ny*nx
   int sm_count;
   int max_smem_optin;
+  int last_kernel[3];  // HS2_K_* of the last sweep per axis (hs2_plan_last_kernel)
 };
 
 void hs2_set_error(const char *fmt, ...);
@@ -68,6 +69,3 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                       const double *halo_hi, int part, cudaStream_t st);
-// kernels_xm.cu - z-marching variant of the folded x sweep (HS2_FLAG_X_MARCH); *done = false: not applicable
-int hs2_tile_sweep_xm(hs2_plan *p, const double *T, double *W, cudaStream_t st, bool *done);
-bool hs2_tile_xm_supported(const hs2_plan *p);

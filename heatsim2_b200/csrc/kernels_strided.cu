@@ -292,6 +292,7 @@ template <int M, bool FINAL>
 int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double *Tin, double *Tout, int L,
                int64_t stride, int n_groups, int lines_per_group, int64_t group_stride, cudaStream_t st, bool *done) {
   *done = false;
+  const int axis = FINAL ? 2 : 1;
   const int P = ax.n_chunks;
   constexpr int W = 16;
   // up to 16 chunks: 256-thread blocks, two per SM; up to 32 chunks (lines of
@@ -337,6 +338,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
     kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+    pl->last_kernel[axis] = big ? HS2_K_TILE_TMA_BIG : HS2_K_TILE_TMA;
   } else {
     // 16-byte cp.async pieces: every row start must be 16-byte aligned
     if ((lines_per_group & 1) || (stride & 1) || (group_stride & 1) || (reinterpret_cast<uintptr_t>(data) & 15)) return HS2_OK;
@@ -346,6 +348,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
     kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+    pl->last_kernel[axis] = big ? HS2_K_TILE_CPASYNC_BIG : HS2_K_TILE_CPASYNC;
   }
   HS2_CUDA_CHECK(cudaGetLastError());
   *done = true;
@@ -387,6 +390,7 @@ int dispatch(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const double
     case 32: rc = launch_tma<32, FINAL>(pl, ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st, &done); break;
   }
   if (rc || done) return rc;
+  pl->last_kernel[FINAL ? 2 : 1] = HS2_K_TILE;
   switch (ax.chunk) {
     case 8: return launch<8, FINAL>(ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st);
     case 16: return launch<16, FINAL>(ax, data, Tin, Tout, L, stride, n_groups, lines_per_group, group_stride, st);
@@ -605,6 +609,7 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
   HS2_REQUIRE(line0 >= 0 && n_lines > 0 && line0 + n_lines <= d.ny * d.nx, "distributed z sweep: bad line range");
   HS2_REQUIRE(n_peers >= 0 && n_peers <= HS2_MAX_Z_PEERS && (n_peers == 0 || peer_y), "distributed z sweep: %d peers (max %d)",
               n_peers, HS2_MAX_Z_PEERS);
+  pl->last_kernel[2] = HS2_K_Z_SLAB;
   ZPeers peers;
   peers.n = n_peers;
   for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;

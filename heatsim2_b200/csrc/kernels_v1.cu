@@ -110,6 +110,7 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
   SrcTable tab;
   int rc = make_src_table(src, &tab);
   if (rc) return rc;
+  p->last_kernel[0] = HS2_K_WHOLE_LINE;
   const hs2_plan_desc &d = p->d;
   const int threads = 256;
   int64_t blocks64 = (p->n + threads - 1) / threads;
@@ -132,6 +133,7 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
 }
 
 int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st) {
+  p->last_kernel[1] = HS2_K_WHOLE_LINE;
   const hs2_plan_desc &d = p->d;
   const int64_t n_lines = d.nz * d.nx;
   thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, nullptr, nullptr, d.axis[1].d_line_id, d.axis[1].d_lu,
@@ -141,6 +143,7 @@ int hs2_v1_sweep_y(hs2_plan *p, double *W, cudaStream_t st) {
 }
 
 int hs2_v1_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st) {
+  p->last_kernel[2] = HS2_K_WHOLE_LINE;
   const hs2_plan_desc &d = p->d;
   const int64_t n_lines = d.ny * d.nx;
   thomas_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, st>>>(W, T, Tout, d.axis[2].d_line_id, d.axis[2].d_lu, n_lines,

@@ -443,12 +443,7 @@ int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source 
   SrcTab tabsrc;
   int rc = hs2_make_src_tab(src, &tabsrc);
   if (rc) return rc;
-  if ((p->d.flags & HS2_FLAG_X_MARCH) && part == 0 && !halo_lo && !halo_hi && tabsrc.n == 0 && !(src && src->d_dense)) {
-    // source-free whole-grid sweep: the z-marching kernel (kernels_xm.cu) when the grid fits it
-    bool done = false;
-    rc = hs2_tile_sweep_xm(p, T, W, st, &done);
-    if (rc || done) return rc;
-  }
+  p->last_kernel[0] = HS2_K_X_FOLD;
   if (p->d.class_id_bytes == 1) return dispatch_xf<uint8_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
   return dispatch_xf<uint16_t>(p, T, W, src, tabsrc, halo_lo, halo_hi, part, st);
 }

@@ -2,22 +2,11 @@
 #pragma once
 #include "chunk_core.cuh"
 
-constexpr int HS2_XR = 8;  // x-lines per block tile
-
 struct SrcTab {  // active volumetric classes of this step (<= 8)
   int n;
   uint8_t idx[8];
   double val[8];
 };
-
-// row pitch (doubles) of the chunk-padded shared-memory tile: cell (r, i) lives
-// at r*Sr + i + i/M; Sr = 2 (mod 16) makes the chunk-major accesses of phase 2
-// (lanes = 8 lines x 4 chunks) conflict free for 8-byte words
-__host__ __device__ inline int hs2_row_pitch(int P, int M) {
-  int s = P * (M + 1);
-  while ((s & 15) != 2) ++s;
-  return s;
-}
 
 inline int hs2_make_src_tab(const hs2_source *src, SrcTab *st) {
   st->n = 0;

@@ -140,6 +140,8 @@ def _u64_list(vals):
 class DistPlan(object):
     """Slab plan + the communication of one rank."""
 
+    CHECK_EVERY = 64       # steps between reads of the peer-wait status word
+
     def __init__(self, plan, group=None):
         self.plan = plan
         self.group = group
@@ -158,7 +160,10 @@ class DistPlan(object):
         self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
         self._bufs = {}
         self.use_p2p = os.environ.get("HS2_DIST_P2P", "1") != "0"
-        self.p2p_timeout = float(os.environ.get("HS2_DIST_TIMEOUT_S", "20"))
+        # upper bound of a flag wait.  Ranks of one job drift apart by far more than a
+        # step (I/O, compilation, a debugger) without anything being wrong, so the default
+        # is long; a wait that does expire is fatal (check() raises, close() raises)
+        self.p2p_timeout = float(os.environ.get("HS2_DIST_TIMEOUT_S", "1800"))
         self._px = None
         self.profile = None          # list: when set, _step_p2p appends 7 CUDA events per step
 
@@ -282,8 +287,12 @@ class DistPlan(object):
     def close(self):
         if self._px is not None:
             torch.cuda.synchronize()
+            bad = self._px.status() != 0
             self._px.close()
             self._px = None
+            if bad:
+                raise RuntimeError("heatsim2_b200.dist: a peer did not deliver its data within %.0f s; "
+                                   "fields computed since are invalid" % self.p2p_timeout)
 
     # ------------------------------------------------------- communication
     def exchange_halos(self, T_in):
@@ -377,8 +386,19 @@ class DistPlan(object):
         if Tarray.dtype != torch.float64:
             raise ValueError("Tarray must be float64")
         T_in = Tarray.contiguous()
+        if out is not None:
+            AdiPlan.check_out(out, T_in)
         T_out = torch.empty_like(T_in) if out is None else out
-        return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
+        if not T_in.is_cuda:
+            return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
+        with torch.cuda.device(T_in.device):
+            self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)
+            # a peer that never delivered must not go unnoticed: the waits give up after
+            # p2p_timeout and set a status word; it is read (one device synchronisation)
+            # every CHECK_EVERY steps, by check() and by close()
+            if self._px is not None and self._px.step_no % self.CHECK_EVERY == 0:
+                self.check()
+        return T_out
 
     # bytes this rank sends per step (for NVLink accounting in bench.py)
     def comm_bytes_per_step(self):

@@ -12,6 +12,38 @@ METRIC = "ADI cell-updates/s (float64)"
 UNIT = "cell-updates/s"
 
 
+def field_by_global_index(k0, k1, ny, nx, device, seed=1234):
+    """T0[k,j,i] in [0,1) as a function of the GLOBAL flat cell index only (SURVEY 8d C5:
+    rank-independent generation), so that an N-GPU run and a 1-GPU run of the same grid start
+    from the same field.  splitmix64-style integer mix evaluated with wrapping int64 arithmetic
+    on the device, one plane block at a time."""
+    out = torch.empty((k1 - k0, ny, nx), dtype=torch.float64, device=device)
+    plane = ny * nx
+    m53 = (1 << 53) - 1
+
+    def lsr(x, s):       # logical shift right of an int64 bit pattern
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    def c(v):            # 64-bit constant as a signed python int
+        return v - (1 << 64) if v >= (1 << 63) else v
+    step = max(1, (1 << 24) // plane)
+    for a in range(k0, k1, step):
+        b = min(k1, a + step)
+        x = torch.arange(a * plane, b * plane, dtype=torch.int64, device=device) + c((0x9E3779B97F4A7C15 * (seed + 1)) & ((1 << 64) - 1))
+        x = (x ^ lsr(x, 30)) * c(0xBF58476D1CE4E5B9)
+        x = (x ^ lsr(x, 27)) * c(0x94D049BB133111EB)
+        x = x ^ lsr(x, 31)
+        out[a - k0:b - k0] = (lsr(x, 11) & m53).to(torch.float64).mul_(1.0 / (1 << 53)).view(b - a, ny, nx)
+    return out
+
+
+def _global_sum(T):
+    """sum over all ranks' slabs, compensated: (sum of per-plane sums) in float64"""
+    s = T.sum(dim=(1, 2)).sum().reshape(1)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return float(s)
+
+
 def run(args, shape, workload_name, clock_sampler=None):
     import heatsim2_b200 as hs
     from heatsim2_b200 import _cabi, dist as hdist
@@ -33,8 +65,7 @@ def run(args, shape, workload_name, clock_sampler=None):
     k0, k1 = P.slab
     n_local = (k1 - k0) * shape[1] * shape[2]
     n_global = shape[0] * shape[1] * shape[2]
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    Ta = torch.rand((k1 - k0,) + tuple(shape[1:]), dtype=torch.float64, device=dev, generator=g)
+    Ta = field_by_global_index(k0, k1, shape[1], shape[2], dev)
     Tb = torch.empty_like(Ta)
     ve = prob["volumetric_elements"][k0:k1]
     vol = prob["volumetric"]
@@ -46,6 +77,7 @@ def run(args, shape, workload_name, clock_sampler=None):
         hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
         Ta, Tb = Tb, Ta
         it += 1
+    sum_before = _global_sum(Ta)
     sampler = None
     if clock_sampler is not None and rank == 0:      # nvidia-smi clocks / throttle reasons of rank 0's GPU during the timed region
         sampler = clock_sampler(local)
@@ -70,6 +102,33 @@ def run(args, shape, workload_name, clock_sampler=None):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
     dplan.check()
+    # uniform material in an insulated box: a source-free step conserves sum(T) exactly
+    sum_after = _global_sum(Ta)
+    check = {"sum_T_before": sum_before, "sum_T_after": sum_after,
+             "rel_drift": abs(sum_after - sum_before) / abs(sum_before), "steps": args.steps,
+             "field": "T0 = mix64(global cell index), rank-independent"}
+    check["conserved"] = check["rel_drift"] <= 1e-12
+    # N <= 2 (or HS2_BENCH_CHECK_1GPU=1): the same grid on ONE GPU (this rank's) from the same field,
+    # same number of steps; max relative difference on this rank's slab, max over ranks
+    want_1gpu = os.environ.get("HS2_BENCH_CHECK_1GPU", "1" if world <= 2 else "0") == "1"
+    if want_1gpu:
+        n_cmp = 3
+        P1, S1 = hs.setup(*prob["setup_args"])
+        A = field_by_global_index(0, shape[0], shape[1], shape[2], dev)
+        B = torch.empty_like(A)
+        a, b = A[k0:k1].clone(), torch.empty_like(Ta)
+        for s in range(n_cmp):
+            hs.run_adi_steps(P1, S1, s * dt, dt, A, prob["volumetric_elements"], vol, out=B)
+            A, B = B, A
+            hs.run_adi_steps(P, S, s * dt, dt, a, ve, vol, out=b)
+            a, b = b, a
+        diff = ((a - A[k0:k1]).abs().max() / A.abs().max()).reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        check["vs_1gpu_max_rel_diff"] = float(diff)
+        check["vs_1gpu_steps"] = n_cmp
+        check["vs_1gpu_ok"] = float(diff) <= 1e-13
+        del P1, S1, A, B, a, b
+        torch.cuda.empty_cache()
     # per-phase device times of a few extra steps (peer-memory transport only; not part of the timed region)
     phase_ms = None
     if dplan._px is not None:
@@ -112,7 +171,8 @@ def run(args, shape, workload_name, clock_sampler=None):
         bytes_cell = 64          # distributed z-sweep reads the increment twice: 16 + 16 + 8 + 24
         comm = dplan.comm_bytes_per_step()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": getattr(args, "scaling", "weak"), "check": check,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(tuple(shape)), "grid": list(shape), "cells": n_global,
                            "cells_per_gpu": n_local, "decomposition": "z-slabs, %d planes per GPU" % (k1 - k0),

@@ -178,9 +178,6 @@ def interface_band(GE, tol=1e-16):
     return int((dist[None, :, :] * sig).max()) if sig.any() else 0
 
 
-X_KERNEL_DEFAULT = "fold"      # "march" once measured faster on B200 (profiles/NOTES_r01.md)
-
-
 class AdiPlan(object):
     """One problem (or one z-slab of it) compiled for the CUDA library.
 
@@ -188,6 +185,8 @@ class AdiPlan(object):
     ``[k0, k0 + shape[0])`` of a larger grid split along z over several GPUs:
     x- and y-line tables come from the local planes, z-line tables from the
     global lines (the z-solve spans all slabs, see ``dist.py``)."""
+
+    MAX_TABLE_SOURCES = 8      # hs2_source table form (x_common.cuh SrcTab)
 
     def __init__(self, shape, class_id, class_coef, dt, volume_array, volumetric_elements=None,
                  materials=None, slab=None):
@@ -221,10 +220,6 @@ class AdiPlan(object):
         self._handle = None
         # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
         self.flags = 1 if os.environ.get("HS2_FORCE_FALLBACK", "0") == "1" else 0
-        # HS2_X_KERNEL=march: z-marching shared-memory-ring x kernel (HS2_FLAG_X_MARCH) for
-        # source-free whole-grid sweeps; =fold: kernels_xf.cu everywhere
-        if os.environ.get("HS2_X_KERNEL", X_KERNEL_DEFAULT) == "march":
-            self.flags |= 2
         self._bufs = {}
         self._vol_dev = None
         self._vol_key = None
@@ -293,9 +288,16 @@ class AdiPlan(object):
 
     @property
     def x_kernel(self):
-        """'whole-line', 'fold' or 'march': the kernel a source-free hs2_sweep_x of this plan runs"""
+        """'whole-line' or 'fold': the kernel a whole-grid hs2_sweep_x of this plan runs"""
         self.ensure_device()
-        return ("whole-line", "fold", "march")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
+        return ("whole-line", "fold")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
+
+    def last_kernels(self):
+        """names of the kernel variants the last x, y and z sweeps of this plan launched
+        (hs2_plan_last_kernel): the parity tests assert the path they mean to cover"""
+        self.ensure_device()
+        lib = _cabi.lib()
+        return tuple(lib.hs2_kernel_name(lib.hs2_plan_last_kernel(self._handle, a)).decode() for a in range(3))
 
     @property
     def n_unique(self):
@@ -373,9 +375,27 @@ class AdiPlan(object):
 
     # ------------------------------------------------------------- sources
     def _source(self, t, dt, volumetric_elements, volumetric):
+        """Sources of the step at time ``t`` as the C ABI's hs2_source.  Returns
+        (Source struct or None, keep-alive list)."""
+        table, dense = self.evaluate_sources(t, dt, volumetric_elements, volumetric)
+        if table is None and dense is None:
+            return None, None
+        src = _cabi.Source()
+        keep = [table]
+        if table is not None:
+            src.d_vol_elements = self._vol_elements_dev(volumetric_elements).data_ptr()
+            src.h_value = table.ctypes.data_as(_cabi.c_double_p)
+        if dense is not None:
+            d = torch.from_numpy(np.ascontiguousarray(dense)).to(self._dev)
+            keep.append(d)
+            src.d_dense = d.data_ptr()
+        return src, keep
+
+    def evaluate_sources(self, t, dt, volumetric_elements, volumetric):
         """Evaluate the volumetric sources active at time ``t`` (reference
-        alternatingdirection_c_pyx.pyx:294-386).  Returns (Source struct or
-        None, keep-alive list)."""
+        alternatingdirection_c_pyx.pyx:294-386) on the host.  Returns
+        ``(table, dense)``: a 256-entry W/m^3 value per volumetric class (at most
+        MAX_TABLE_SOURCES non-zero) and/or a dense [nz,ny,nx] array; None when absent."""
         from . import (IMPULSE_SOURCE, STEPPED_SOURCE, IMPULSE_POINT_SOURCE_JOULES,
                        SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE, NO_SOURCE)
         table = np.zeros(256)
@@ -408,7 +428,12 @@ class AdiPlan(object):
                     joulesperm2 = float(joulesperm2)
                     characlength = float(characlength)
                     assert characlength > 0
-                    centre = np.asarray(z_ndgrid) * decaydirec[0] - offset
+                    z_ndgrid = np.asarray(z_ndgrid)
+                    if self.slab is not None and z_ndgrid.ndim == 3 and z_ndgrid.shape[0] == self.slab["nz_global"] \
+                            and z_ndgrid.shape[0] != self.shape[0]:
+                        # the tuple describes the global grid; this plan owns planes [k0, k0 + nz)
+                        z_ndgrid = z_ndgrid[self.slab["k0"]:self.slab["k0"] + self.shape[0]]
+                    centre = z_ndgrid * decaydirec[0] - offset
                     left = centre - decay_dz / 2.0
                     right = centre + decay_dz / 2.0
                     use = (_to_numpy(volumetric_elements) == idx) & (right > 0.0)
@@ -418,18 +443,13 @@ class AdiPlan(object):
                     dense[use] = frac * joulesperm2 / (decay_dz * dt)
             else:
                 raise ValueError("unknown volumetric source type %r" % (kind,))
-        if not table.any() and dense is None:
-            return None, None
-        src = _cabi.Source()
-        keep = [table]
-        if table.any():
-            src.d_vol_elements = self._vol_elements_dev(volumetric_elements).data_ptr()
-            src.h_value = table.ctypes.data_as(_cabi.c_double_p)
-        if dense is not None:
-            d = torch.from_numpy(np.ascontiguousarray(dense)).to(self._dev)
-            keep.append(d)
-            src.d_dense = d.data_ptr()
-        return src, keep
+        if np.count_nonzero(table) > self.MAX_TABLE_SOURCES:
+            # the kernels' table form holds 8 classes; more simultaneously active regions
+            # (the reference allows all 256, alternatingdirection_c_pyx.pyx:301-383) go dense
+            dense = np.zeros(self.shape) if dense is None else dense
+            dense += table[_to_numpy(volumetric_elements)]
+            table[:] = 0.0
+        return (table if table.any() else None), dense
 
     def _vol_elements_dev(self, volumetric_elements):
         if isinstance(volumetric_elements, torch.Tensor) and volumetric_elements.is_cuda:
@@ -471,6 +491,16 @@ class AdiPlan(object):
         if tuple(T.shape) != self.shape:
             raise ValueError("Tarray has shape %r, the plan was set up for %r" % (tuple(T.shape), self.shape))
 
+    @staticmethod
+    def check_out(out, like):
+        """``out=`` goes to the kernels as a raw pointer: it has to look exactly like the input"""
+        if not isinstance(out, torch.Tensor):
+            raise TypeError("out must be a torch tensor")
+        if out.shape != like.shape or out.dtype != like.dtype or out.device != like.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor of shape %r on %s (got %s %r on %s, contiguous=%s)"
+                             % (like.dtype, tuple(like.shape), like.device, out.dtype, tuple(out.shape), out.device,
+                                out.is_contiguous()))
+
     def timed_sweeps(self, T_in, T_out, events):
         """One source-free step as three separate C-ABI calls with CUDA events
         recorded on the launching stream between them (bench.py's per-kernel
@@ -501,6 +531,8 @@ class AdiPlan(object):
                 self.step_device(d_T, d_T, t, dt, volumetric_elements, volumetric)
                 if out is None:
                     out = torch.empty(self.shape, dtype=torch.float64).pin_memory()
+                else:
+                    self.check_out(out, Tarray)
                 out.copy_(d_T, non_blocking=True)
                 torch.cuda.current_stream(self._dev).synchronize()
             return out
@@ -509,6 +541,8 @@ class AdiPlan(object):
             if Tarray.dtype != torch.float64:
                 raise ValueError("Tarray must be float64")
             T_in = Tarray.contiguous()
+            if out is not None:
+                self.check_out(out, T_in)
             with torch.cuda.device(T_in.device):
                 T_out = torch.empty_like(T_in) if out is None else out
                 return self.step_device(T_in, T_out, t, dt, volumetric_elements, volumetric)

@@ -106,7 +106,6 @@ typedef struct hs2_plan_desc {
 } hs2_plan_desc;
 
 #define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
-#define HS2_FLAG_X_MARCH 2        /* x sweep: z-marching shared-memory-ring kernel for source-free whole-grid sweeps */
 
 typedef struct hs2_plan hs2_plan;
 
@@ -133,13 +132,27 @@ int hs2_plan_destroy(hs2_plan *plan);
 /* number of kernels one hs2_step launches with this plan                     */
 int hs2_plan_launches_per_step(const hs2_plan *plan);
 
-/* which kernel a source-free whole-grid hs2_sweep_x of this plan runs:
- * whole-line global-memory fallback (rhs + Thomas), folded tile kernel, or
- * the z-marching shared-memory-ring kernel (HS2_FLAG_X_MARCH)                */
+/* which kernel a whole-grid hs2_sweep_x of this plan runs: whole-line
+ * global-memory fallback (rhs + Thomas) or the folded tile kernel            */
 #define HS2_XK_WHOLE_LINE 0
 #define HS2_XK_FOLD 1
-#define HS2_XK_MARCH 2
 int hs2_plan_x_kernel(const hs2_plan *plan);
+
+/* Which kernel variant the LAST sweep along `axis` (0 = x, 1 = y, 2 = z) of
+ * this plan launched: one of HS2_K_* (0 before the first sweep).  Lets a
+ * caller - and the parity tests - verify that a given grid ran on the code
+ * path it was meant to exercise.  hs2_kernel_name gives the code's name.      */
+#define HS2_K_NONE 0
+#define HS2_K_WHOLE_LINE 1     /* kernels_v1.cu: one thread per line, global memory      */
+#define HS2_K_TILE 2           /* strided_sweep: register tile, one block per tile       */
+#define HS2_K_TILE_TMA 3       /* strided_sweep_tma: persistent, next tile by TMA        */
+#define HS2_K_TILE_TMA_BIG 4   /* the same with 512-thread blocks (17..32 chunks)        */
+#define HS2_K_TILE_CPASYNC 5   /* persistent, next tile by 16-byte cp.async              */
+#define HS2_K_TILE_CPASYNC_BIG 6
+#define HS2_K_X_FOLD 7         /* sweep_xf_kernel                                        */
+#define HS2_K_Z_SLAB 8         /* z_forward / z_backward of a slab plan                  */
+int hs2_plan_last_kernel(const hs2_plan *plan, int axis);
+const char *hs2_kernel_name(int code);
 
 /* One ADI time step = run_adi_steps (alternatingdirection_c_pyx.pyx:287-416).
  *   d_T_in   [nz][ny][nx]  field at t - dt/2

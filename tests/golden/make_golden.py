@@ -11,6 +11,13 @@ Each file holds, for one tests/problems.py configuration, the field after the
 listed step counts (``T_<n>``), the whole-run history at the probe cells
 (``probe_hist``, when the problem names probes) and ``sum_<n>``; inputs are NOT
 stored - they are rebuilt from tests/problems.py with the recorded kwargs.
+
+BIG cases (SURVEY.md 8(d) sizes: C2 at 64^3 and 128^3 for 1000 steps, C3 at
+128^3, C4 at 64x128x128) store a compact digest instead of the field
+(tests/util.py ``digest``): the field sub-sampled with stride ``sub`` in every
+direction, its sum, four dot products with seeded random weight fields (an error
+anywhere in the field moves them) and, for C4, the per-step history of
+surface_temperature.insulating_z_min_surface_temperature at a few columns.
 """
 import json
 import os
@@ -40,11 +47,51 @@ CASES = {
 }
 
 
+# name -> (problem, kwargs, steps digested, sub-sampling stride, surface-history columns or None)
+BIG = {
+    "big_c2_uniform_64": ("uniform_slab", dict(n=64, nsteps=1000), (1, 100, 1000), 4, None),
+    "big_c2_uniform_128": ("uniform_slab", dict(n=128, nsteps=1000), (1, 100, 1000), 8, None),
+    "big_c3_steelonwater_128": ("steelonwater", dict(nz=128, ny=128, nx=128, nsteps=200), (1, 20, 200), 8, None),
+    "big_c4_composite_64x128x128": ("composite", dict(nz=64, ny=128, nx=128, ply=8, nsteps=300), (1, 30, 300), 8,
+                                    ((5, 7), (40, 64), (64, 64), (100, 31))),
+}
+
+
+def big(ref, only):
+    import util
+    for case, (pname, kwargs, steps, sub, cols) in BIG.items():
+        if only and case not in only:
+            continue
+        prob = problems.ALL[pname](ref, **kwargs)
+        P, S = ref_loader.quiet_setup(ref, *prob["setup_args"])
+        T = np.array(prob["T0"], dtype=np.float64)
+        out = {"meta": json.dumps({"problem": pname, "kwargs": kwargs, "steps": list(steps), "sub": sub,
+                                   "surface_cols": cols})}
+        hist = []
+        for it in range(prob["nsteps"]):
+            T = ref.run_adi_steps(P, S, prob["t0"] + prob["dt"] * it, prob["dt"], T,
+                                  prob["volumetric_elements"], prob["volumetric"])
+            if cols:
+                surf = ref.surface_temperature.insulating_z_min_surface_temperature(T, prob["dz"])
+                hist.append([surf[c] for c in cols])
+            if (it + 1) in steps:
+                for k, v in util.digest(T, sub).items():
+                    out["%s_%d" % (k, it + 1)] = v
+        if cols:
+            out["surface_hist"] = np.array(hist)
+        np.savez_compressed(os.path.join(HERE, case + ".npz"), **out)
+        print(case, prob["shape"], prob["nsteps"], "steps", flush=True)
+
+
 def main():
     ref = ref_loader.load()
     if ref is None:
         raise SystemExit("reference not built: run python oracle/build_ref.py first")
     only = set(sys.argv[1:])          # optional: names of the cases to (re)generate
+    if "--big" in only or any(o in BIG for o in only):
+        import heatsim2.surface_temperature  # noqa: F401  (not imported by the reference's __init__)
+        big(ref, only - {"--big"})
+        return
     for case, (pname, kwargs, steps) in CASES.items():
         if only and case not in only:
             continue

@@ -68,13 +68,15 @@ def _run(world, name, kwargs, nsteps, env=None, info=None):
     (4, "steelonfoam", dict(nz=64, ny=10, nx=12)),
     (2, "composite", dict(nz=32, ny=12, nx=16, ply=4)),
     (2, "steelonwater", dict(nz=48, ny=20, nx=24)),
+    # all four source kinds; the z-decaying impulse carries a GLOBAL z_ndgrid
+    (2, "sources_demo", dict(nz=16, ny=10, nx=14)),
     # BASELINE configs[4] recipe (uniform steel slab, random T0) on 8 ranks: strongly
     # implicit z-lines, so the interface band spans several 8-plane slabs
     (8, "uniform_slab", dict(shape=(64, 10, 12))),
 ])
 def test_slabs_match_oracle(world, name, kwargs):
     import heatsim2_b200 as hs
-    nsteps = 4
+    nsteps = 6 if name == "sources_demo" else 4
     got = _run(world, name, kwargs, nsteps)
     prob = problems.ALL[name](hs, **kwargs)
     want = adi_oracle.run(prob, nsteps=nsteps)

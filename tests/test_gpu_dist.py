@@ -86,6 +86,7 @@ def _run(world, name, kwargs, nsteps, p2p=True):
     ("steelonfoam", dict(nz=64, ny=40, nx=48), 6),
     ("uniform_slab", dict(shape=(128, 48, 64)), 4),
     ("composite", dict(nz=64, ny=32, nx=32, ply=8), 4),
+    ("sources_demo", dict(nz=16, ny=10, nx=14), 6),
 ])
 def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
     import adi_oracle

@@ -327,3 +327,27 @@ def test_cellwise_assembly_like_the_reference_loop():
     b = Pv.plan.class_coef[Pv.plan.class_id.cpu().numpy().astype(int)]
     assert np.array_equal(a, b)
     assert P.plan.n_unique == Pv.plan.n_unique
+
+
+def test_more_than_eight_active_sources_fold_into_dense():
+    """the table form of hs2_source holds 8 classes; a step with more active
+    regions must fall back to the dense array, not raise"""
+    import heatsim2_b200 as hs
+    prob = problems.uniform_slab(hs, shape=(6, 8, 26))
+    args = list(prob["setup_args"])
+    nsrc = 12
+    volumetric = ((hs.NO_SOURCE,),) + tuple((hs.STEPPED_SOURCE, 0.0, 1.0, 1e6 * (s + 1)) for s in range(nsrc))
+    ve = np.zeros(prob["shape"], dtype=np.uint8)
+    for s in range(nsrc):
+        ve[s % 6, :, 2 * s:2 * s + 2] = s + 1
+    args[12], args[17] = volumetric, ve
+    P, S = hs.setup(*args)
+    table, dense = P.plan.evaluate_sources(0.5, prob["dt"], ve, volumetric)
+    assert table is None
+    want = np.zeros(prob["shape"])
+    for s in range(nsrc):
+        want[ve == s + 1] = 1e6 * (s + 1)
+    assert np.array_equal(dense, want)
+    # 8 or fewer stay in table form
+    table, dense = P.plan.evaluate_sources(0.5, prob["dt"], ve, volumetric[:9])
+    assert dense is None and np.count_nonzero(table) == 8

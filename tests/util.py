@@ -15,6 +15,34 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
 
+def digest(T, sub):
+    """Compact digest of a field (big golden cases): sub-sampled values, sum and
+    four dot products with seeded uniform(-1,1) weight fields; ``wabs`` = sum of
+    |w*T| of the first one sets the scale of the dot-product tolerance."""
+    T = np.asarray(T)
+    out = {"sub": T[::sub, ::sub, ::sub].copy(), "sum": T.sum(), "absmax": np.abs(T).max()}
+    dots = []
+    for s in range(4):
+        w = np.random.default_rng(1000 + s).uniform(-1.0, 1.0, T.shape)
+        dots.append(float((w * T).sum()))
+        if s == 0:
+            out["wabs"] = float(np.abs(w * T).sum())
+    out["dots"] = np.array(dots)
+    return out
+
+
+def check_digest(T, z, step, sub, tol):
+    """Assert that field ``T`` matches the digest stored for ``step``."""
+    d = digest(T, sub)
+    want = z["sub_%d" % step]
+    scale = float(z["absmax_%d" % step])
+    assert float(np.abs(d["sub"] - want).max()) <= tol * scale, ("sub", step, float(np.abs(d["sub"] - want).max()) / scale)
+    assert abs(d["sum"] - float(z["sum_%d" % step])) <= tol * T.size * scale, ("sum", step)
+    # a dot product of n terms each within tol*scale of the reference
+    lim = tol * scale * np.sqrt(T.size) * 4.0
+    assert float(np.abs(d["dots"] - z["dots_%d" % step]).max()) <= lim, ("dots", step, float(np.abs(d["dots"] - z["dots_%d" % step]).max()) / lim)
+
+
 def load_golden(case):
     z = np.load(os.path.join(GOLDEN, case + ".npz"))
     meta = json.loads(str(z["meta"]))
@@ -22,7 +50,11 @@ def load_golden(case):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("big_"))
+
+
+def big_golden_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("big_"))
 
 
 def run_b200(hs, prob, nsteps=None, record=None, host_api=False):
