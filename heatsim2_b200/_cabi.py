@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HS2_B200_LIB") or os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -22,6 +22,7 @@ class AxisTables(ctypes.Structure):
     _fields_ = [
         ("d_line_id", c_void_p), ("d_lu", c_void_p),
         ("d_tab", c_void_p), ("d_GE", c_void_p), ("d_tab_il", c_void_p),
+        ("h_utab", c_void_p), ("d_ucode", c_void_p),
         ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
         ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
@@ -52,6 +53,7 @@ _lib = None
 PROTOTYPES = {
     "hs2_abi_version": (ctypes.c_int, []),
     "hs2_last_error": (ctypes.c_char_p, []),
+    "hs2_sizeof": (ctypes.c_int, [ctypes.c_int]),
     "hs2_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.POINTER(c_void_p)]),
     "hs2_plan_destroy": (ctypes.c_int, [c_void_p]),
     "hs2_plan_launches_per_step": (ctypes.c_int, [c_void_p]),
@@ -99,6 +101,10 @@ def lib():
         if L.hs2_abi_version() != ABI_VERSION:
             raise ImportError("heatsim2_b200: ABI version mismatch (%d != %d); rebuild the library"
                               % (L.hs2_abi_version(), ABI_VERSION))
+        for which, struct in enumerate((AxisTables, PlanDesc, Source)):
+            if L.hs2_sizeof(which) != ctypes.sizeof(struct):
+                raise ImportError("heatsim2_b200: ctypes mirror of %s is %d bytes, the library's struct %d"
+                                  % (struct.__name__, ctypes.sizeof(struct), L.hs2_sizeof(which)))
         _lib = L
     return _lib
 

@@ -19,6 +19,15 @@ int hs2_abi_version(void) { return HS2_ABI_VERSION; }
 
 const char *hs2_last_error(void) { return g_err; }
 
+int hs2_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(hs2_axis_tables);
+    case 1: return (int)sizeof(hs2_plan_desc);
+    case 2: return (int)sizeof(hs2_source);
+  }
+  return -1;
+}
+
 int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
   HS2_REQUIRE(desc && out, "hs2_plan_create: NULL argument");
   *out = nullptr;
@@ -49,6 +58,15 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   p->last_kernel[0] = p->last_kernel[1] = p->last_kernel[2] = HS2_K_NONE;
+  for (int a = 0; a < 3; ++a) {
+    const hs2_axis_tables &ax = desc->axis[a];
+    memset(&p->utab[a], 0, sizeof(UTab));
+    p->has_utab[a] = ax.h_utab && ax.d_ucode && ax.chunk > 0 && ax.chunk <= 32;
+    if (p->has_utab[a])
+      for (int pl = 0; pl < HS2_T_PLANES; ++pl)
+        for (int t = 0; t < ax.chunk; ++t) p->utab[a].v[pl][t] = ax.h_utab[pl * ax.chunk + t];
+    p->d.axis[a].h_utab = nullptr;   // the caller's buffer is not referenced after this call
+  }
   *out = p;
   return HS2_OK;
 }
@@ -60,11 +78,12 @@ int hs2_plan_destroy(hs2_plan *plan) {
 
 int hs2_plan_launches_per_step(const hs2_plan *plan) {
   if (!plan) return 0;
-  return (hs2_tile_xf_supported(plan) ? 1 : 2) + 2;
+  return ((hs2_tile_xt_supported(plan) || hs2_tile_xf_supported(plan)) ? 1 : 2) + 2;
 }
 
 int hs2_plan_x_kernel(const hs2_plan *plan) {
   if (!plan) return -1;
+  if (hs2_tile_xt_supported(plan)) return HS2_XK_TMA;
   if (!hs2_tile_xf_supported(plan)) return HS2_XK_WHOLE_LINE;
   return HS2_XK_FOLD;
 }
@@ -76,7 +95,7 @@ int hs2_plan_last_kernel(const hs2_plan *plan, int axis) {
 
 const char *hs2_kernel_name(int code) {
   static const char *const names[] = {"none", "whole-line", "tile", "tile-tma", "tile-tma-512", "tile-cpasync",
-                                      "tile-cpasync-512", "x-fold", "z-slab"};
+                                      "tile-cpasync-512", "x-fold", "z-slab", "x-tma"};
   return (code >= 0 && code < (int)(sizeof(names) / sizeof(names[0]))) ? names[code] : "?";
 }
 
@@ -84,6 +103,11 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
                 const double *d_halo_hi, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
+  if (hs2_tile_xt_supported(plan)) {
+    bool done = false;
+    int rc = hs2_tile_sweep_xt(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream, &done);
+    if (rc || done) return rc;
+  }
   if (hs2_tile_xf_supported(plan))
     return hs2_tile_sweep_xf(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream);
   return hs2_v1_sweep_x(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, (cudaStream_t)stream);
@@ -94,6 +118,11 @@ int hs2_sweep_x_part(hs2_plan *plan, const double *d_T_in, double *d_work, const
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x_part: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x_part: d_work must not alias d_T_in");
   HS2_REQUIRE(part == HS2_X_INTERIOR || part == HS2_X_BOUNDARY, "hs2_sweep_x_part: part must be HS2_X_INTERIOR or HS2_X_BOUNDARY");
+  if (hs2_tile_xt_supported(plan) && plan->d.nz >= 3) {
+    bool done = false;
+    int rc = hs2_tile_sweep_xt(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, part, (cudaStream_t)stream, &done);
+    if (rc || done) return rc;
+  }
   if (!hs2_tile_xf_supported(plan) || plan->d.nz < 3) {
     // kernels without plane ranges: everything happens in the boundary call
     if (part == HS2_X_INTERIOR) return HS2_OK;

@@ -105,6 +105,51 @@ __device__ __forceinline__ void chunk_backward_short(double (&v)[M], const doubl
   }
 }
 
+// ---------------------------------------------------------------------------
+// Uniform-chunk fast path.  The chunk-local factorisation restarts at every
+// chunk start, so all interior chunks of a line with constant coefficients have
+// bit-identical factor tables (and so do the interior chunks of every other
+// line through the same material).  The host finds the most common chunk table
+// of an axis (plan.py uniform_chunks), the kernels receive it BY VALUE as a
+// __grid_constant__ parameter - i.e. in the constant bank - and a warp whose
+// chunks all carry it reads every factor as a constant operand of the DFMA
+// itself: no load instruction, no L1/shared-memory wavefront.  Measured in
+// round 1 (profiles/kernels_r01e.md): the broadcast table loads were 85 % of
+// the L1 data-pipe wavefronts of the y sweep and a third of the x sweep's.
+// Same values, same operation order => bit-identical to the table-load path.
+// (struct UTab: hs2_common.cuh)
+template <int M>
+__device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab &ut) {
+#pragma unroll
+  for (int t = 0; t < M; ++t) v[t] *= ut.v[HS2_T_INV][t];
+  double prev = 0.0;
+#pragma unroll
+  for (int t = 0; t < M; ++t) {
+    prev = fma(-ut.v[HS2_T_F][t], prev, v[t]);
+    v[t] = prev;
+  }
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int t = 0; t < M; t += 2) {
+    a0 = fma(ut.v[HS2_T_C][t], v[t], a0);
+    a1 = fma(ut.v[HS2_T_C][t + 1], v[t + 1], a1);
+  }
+  return a0 + a1;
+}
+
+template <int M>
+__device__ __forceinline__ void chunk_backward_const(double (&v)[M], const UTab &ut, double alpha, double E) {
+#pragma unroll
+  for (int t = 0; t < M; ++t) v[t] = fma(-alpha, ut.v[HS2_T_S][t], v[t]);
+  double nxt = E;
+  v[M - 1] = E;
+#pragma unroll
+  for (int t = M - 2; t >= 0; --t) {
+    nxt = fma(-ut.v[HS2_T_CP][t], nxt, v[t]);
+    v[t] = nxt;
+  }
+}
+
 // E_p = row p of the inverse interface operator applied to the interleaved
 // (yf_0, yl_0, yf_1, yl_1, ...) values of this line held in Y[2P][ld] column w.
 // The operator decays geometrically away from the diagonal; `band` (from the

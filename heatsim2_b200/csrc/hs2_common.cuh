@@ -7,12 +7,19 @@
 
 #include "../../include/hs2_b200.h"
 
+// the most common chunk table of an axis, handed to the kernels by value (chunk_core.cuh)
+struct UTab {
+  double v[HS2_T_PLANES][32];   // [plane][row in chunk], rows >= chunk unused
+};
+
 struct hs2_plan {
   hs2_plan_desc d;
   int64_t n;           // nz*ny*nx
   int sm_count;
   int max_smem_optin;
   int last_kernel[3];  // HS2_K_* of the last sweep per axis (hs2_plan_last_kernel)
+  UTab utab[3];        // copy of axis[a].h_utab (passed to the kernels by value)
+  bool has_utab[3];
 };
 
 void hs2_set_error(const char *fmt, ...);
@@ -65,7 +72,11 @@ int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
               int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st);
-// kernels_xf.cu - x sweep with the explicit x-term folded into the solve (default)
+// kernels_xt.cu - x sweep on TMA-staged patches (default where it applies); *done = false: fall through
+bool hs2_tile_xt_supported(const hs2_plan *p);
+int hs2_tile_sweep_xt(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
+                      const double *halo_hi, int part, cudaStream_t st, bool *done);
+// kernels_xf.cu - x sweep with the explicit x-term folded into the solve
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                       const double *halo_hi, int part, cudaStream_t st);

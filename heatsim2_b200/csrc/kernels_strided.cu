@@ -122,9 +122,14 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
 // buffer is handed back to the copy engine.  Results are stored straight from
 // registers.  Tensor map: rank 3, dims (n0, n1, n2) = (nx, ny, nz) for the
 // y-sweep and (ny*nx, nz, 1) for the z-sweep, box (W, BR, 1).
-template <int M, int W, bool FINAL, bool USE_TMA, bool BIG>
+// UT: warps whose chunks all carry the axis' most common table read the factors as constant operands
+// (chunk_core.cuh).  Measured on B200 at 512^3 (scripts/ab_sweeps.py, one run): z sweep 0.641 -> 0.613 ms,
+// y sweep 0.377 -> 0.401 ms (it is HBM-bound already and the uniform loads add latency) - so UT is
+// instantiated for the z sweep only.
+template <int M, int W, bool FINAL, bool USE_TMA, bool BIG, bool UT>
 __global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 2)
-strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__ data, const double *__restrict__ Tin,
+strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UTab ut,
+                  const uint8_t *__restrict__ ucode, double *__restrict__ data, const double *__restrict__ Tin,
                   double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
                   const double *__restrict__ GE, int L, int pitch, int P, int band, int64_t stride, int tiles_per_group,
                   int lines_per_group, int64_t group_stride, int n_tiles, int BR, int n_boxes, int do_prefetch) {
@@ -166,7 +171,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
       }
     } else {
       const int nthr = W * P;
-      const int tid = p * W + w;
+      const int tid = threadIdx.y * W + w;
       const double *src0 = data + (int64_t)group * group_stride + c0;
       for (int e = tid; e < L * (W / 2); e += nthr) {
         const int r = e / (W / 2), c = (e % (W / 2)) * 2;
@@ -188,7 +193,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
   uint32_t lid_c = 0xffffffffu;
   if (t < n_tiles) {
     lid_c = line_id[(int64_t)(t / tiles_per_group) * lines_per_group + (t % tiles_per_group) * W];
-    const int tid = p * W + w, nthr = W * P;
+    const int tid = threadIdx.y * W + w, nthr = W * P;
     const double *gt = tab + (int64_t)lid_c * HS2_T_PLANES * pitch;
     for (int e = tid; e < HS2_T_PLANES * pitch; e += nthr) s_tab[e] = gt[e];
     const double *gg = GE + (int64_t)lid_c * P * 2 * P;
@@ -203,6 +208,8 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     const int64_t line = (int64_t)group * lines_per_group + (live ? col : 0);
     const int64_t off = (int64_t)group * group_stride + (live ? col : 0) + (int64_t)r0 * stride;
     const uint32_t lid = line_id[line];
+    // every chunk of this warp carries the axis' common table: factors come from the constant bank
+    const bool uni = UT && ucode != nullptr && __all_sync(0xffffffffu, ucode[(int64_t)lid * P + p] != 0);
     const double *tb = lid == lid_c ? s_tab + r0 : tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
     const double *ge = lid == lid_c ? s_ge + p * (2 * P) : GE + ((int64_t)lid * P + p) * (2 * P);
     if (FINAL && live && do_prefetch && (w & 3) == 0) {
@@ -233,7 +240,10 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     HS2_MARK(2);
     // (16-byte table loads: the 8-byte variant of chunk_core.cuh measured 6 % slower here)
     double yf, last;
-    if (full) {
+    if (UT && uni) {
+      yf = chunk_forward_const<M>(v, ut);
+      last = v[M - 1];
+    } else if (full) {
       yf = chunk_forward_full<M>(v, tb, pitch);
       last = v[M - 1];
     } else {
@@ -248,7 +258,9 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, double *__restrict__
     HS2_MARK(4);
     __syncthreads();
     const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
-    if (full)
+    if (UT && uni)
+      chunk_backward_const<M>(v, ut, alpha, E);
+    else if (full)
       chunk_backward_full<M>(v, tb, pitch, alpha, E);
     else
       chunk_backward_short<M>(v, tb, pitch, rows, alpha, E);
@@ -310,6 +322,7 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   static const int zmode = getenv("HS2_Z_PREFETCH") ? atoi(getenv("HS2_Z_PREFETCH")) : 1;
   if (group_stride == 0 && zmode == 0) return HS2_OK;
   const bool use_tma = group_stride != 0 || zmode == 2;
+  const uint8_t *ucode = (FINAL && pl->has_utab[axis] && !(pl->d.flags & HS2_FLAG_NO_UTAB)) ? ax.d_ucode : nullptr;
   static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 1;
   const int BR = L < 256 ? L : 256;
   const int n_boxes = (L + BR - 1) / BR;
@@ -332,21 +345,21 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
     else
       ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
     if (!ok) return HS2_OK;
-    auto kern = big ? strided_sweep_tma<M, W, FINAL, true, (M >= 32)> : strided_sweep_tma<M, W, FINAL, true, false>;
+    auto kern = big ? strided_sweep_tma<M, W, FINAL, true, (M >= 32), FINAL> : strided_sweep_tma<M, W, FINAL, true, false, FINAL>;
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
-    kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
+    kern<<<grid, block, smem, st>>>(tmap, pl->utab[axis], ucode, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
     pl->last_kernel[axis] = big ? HS2_K_TILE_TMA_BIG : HS2_K_TILE_TMA;
   } else {
     // 16-byte cp.async pieces: every row start must be 16-byte aligned
     if ((lines_per_group & 1) || (stride & 1) || (group_stride & 1) || (reinterpret_cast<uintptr_t>(data) & 15)) return HS2_OK;
-    auto kern = big ? strided_sweep_tma<M, W, FINAL, false, (M >= 32)> : strided_sweep_tma<M, W, FINAL, false, false>;
+    auto kern = big ? strided_sweep_tma<M, W, FINAL, false, (M >= 32), FINAL> : strided_sweep_tma<M, W, FINAL, false, false, FINAL>;
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
     HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
-    kern<<<grid, block, smem, st>>>(tmap, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
+    kern<<<grid, block, smem, st>>>(tmap, pl->utab[axis], ucode, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
                                     stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
     pl->last_kernel[axis] = big ? HS2_K_TILE_CPASYNC_BIG : HS2_K_TILE_CPASYNC;
   }

@@ -64,6 +64,12 @@ def thomas_factors(lo, dg, hi):
     return out
 
 
+def x_tma_applies(nx):
+    """The TMA-fed x sweep (csrc/kernels_xt.cu) takes lines of 16..512 cells, a multiple
+    of 16 (one 128-byte segment per thread); HS2_X_KERNEL=fold keeps the LSU-fed kernel."""
+    return os.environ.get("HS2_X_KERNEL", "tma") != "fold" and nx % 16 == 0 and 16 <= nx <= 512
+
+
 def choose_chunk(L, axis=None):
     """Rows per chunk M and chunk count P for a line of length L.  The kernels
     hold M doubles per thread in registers and run P*W threads per tile
@@ -73,6 +79,8 @@ def choose_chunk(L, axis=None):
     HS2_CHUNK_X for the x axis) with at least 4 chunks is taken, else the
     largest valid M.  (0, 0): too long for the register-tile kernels
     (whole-line fallback)."""
+    if axis == 0 and x_tma_applies(L):
+        return 16, L // 16                 # kernels_xt.cu: one 128-byte segment per thread
     valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
     if not valid:
         return 0, 0
@@ -166,6 +174,39 @@ def interleave_chunks(tab, L, M, P):
     return np.ascontiguousarray(full.reshape(nu, T_PLANES, P, M // 2, 2).transpose(0, 1, 3, 2, 4))
 
 
+def uniform_chunks(tab, L, M, P, line_id=None):
+    """The most common chunk table of an axis and where it applies.
+
+    The chunk-local factorisation of ``chunk_factors`` restarts at every chunk
+    start, so every interior chunk of a line with constant coefficients - and of
+    any other line that crosses the same material there - has bit-identical
+    tables.  Returns ``(utab [T_PLANES, M], ucode uint8 [n_unique, P])`` with
+    ``ucode[u, p] = 1`` where the full chunk p of unique line u equals ``utab``
+    bit for bit; chunks are weighted by the number of lines that use them
+    (``line_id``: int array/tensor of unique-line ids, optional).  The kernels
+    get ``utab`` by value and read it as constant operands (chunk_core.cuh)."""
+    nu = tab.shape[0]
+    n_full = L // M
+    ucode = np.zeros((nu, P), dtype=np.uint8)
+    if n_full == 0:
+        return np.zeros((T_PLANES, M)), ucode
+    if line_id is None:
+        weight = np.ones(nu, dtype=np.int64)
+    else:
+        lid = line_id.cpu().numpy() if isinstance(line_id, torch.Tensor) else np.asarray(line_id)
+        weight = np.bincount(lid.astype(np.int64), minlength=nu)
+    blocks = np.ascontiguousarray(tab[:, :, :n_full * M].reshape(nu, T_PLANES, n_full, M).transpose(0, 2, 1, 3))
+    flat = blocks.reshape(nu * n_full, T_PLANES * M)
+    keys = flat.view(np.dtype((np.void, flat.dtype.itemsize * flat.shape[1]))).reshape(-1)
+    uniq, inverse = np.unique(keys, return_inverse=True)
+    votes = np.bincount(inverse.reshape(-1), weights=np.repeat(weight, n_full).astype(np.float64), minlength=len(uniq))
+    best = int(np.argmax(votes))
+    first = int(np.nonzero(inverse.reshape(-1) == best)[0][0])
+    utab = flat[first].reshape(T_PLANES, M).copy()
+    ucode[:, :n_full] = (inverse.reshape(nu, n_full) == best)
+    return utab, ucode
+
+
 def interface_band(GE, tol=1e-16):
     """Half-width, in chunks, outside which every entry of every GE row is
     below ``tol`` times the row maximum (the interface operator decays
@@ -220,6 +261,13 @@ class AdiPlan(object):
         self._handle = None
         # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
         self.flags = 1 if os.environ.get("HS2_FORCE_FALLBACK", "0") == "1" else 0
+        # HS2_NO_UTAB=1: every chunk reads its factor tables (A/B of the constant-bank fast path)
+        if os.environ.get("HS2_NO_UTAB", "0") == "1":
+            self.flags |= 4
+        if os.environ.get("HS2_X_KERNEL", "tma") == "fold":
+            self.flags |= 16
+        # axes whose kernels take the constant-bank table (measured on B200, profiles/NOTES_r02.md)
+        self.utab_axes = os.environ.get("HS2_UTAB_AXES", "xz")     # x: the TMA-fed kernel; z: strided_sweep_tma<FINAL>
         self._bufs = {}
         self._vol_dev = None
         self._vol_key = None
@@ -290,7 +338,7 @@ class AdiPlan(object):
     def x_kernel(self):
         """'whole-line' or 'fold': the kernel a whole-grid hs2_sweep_x of this plan runs"""
         self.ensure_device()
-        return ("whole-line", "fold")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
+        return ("whole-line", "fold", "tma")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
 
     def last_kernels(self):
         """names of the kernel variants the last x, y and z sweeps of this plan launched
@@ -322,6 +370,7 @@ class AdiPlan(object):
         self.d_line_lu = [torch.from_numpy(t).to(dev).contiguous() for t in self.line_lu]
         self.d_chunk = [None if t is None else [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in t]
                         for t in self.chunk_tabs]
+        self._utab, self._d_ucode = [None] * 3, [None] * 3
         desc = _cabi.PlanDesc()
         desc.nz, desc.ny, desc.nx = self.shape
         desc.n_classes = self.n_classes
@@ -338,6 +387,13 @@ class AdiPlan(object):
                 ax.d_tab, ax.d_GE = (t.data_ptr() for t in self.d_chunk[a])
                 ax.pitch = self.d_chunk[a][0].shape[2]
                 ax.band = interface_band(self.chunk_tabs[a][1])
+                if (not self.slab or a != 2) and "xyz"[a] in self.utab_axes:
+                    Mc, Pc = self.chunk[a]
+                    utab, ucode = uniform_chunks(self.chunk_tabs[a][0], self.shape[2 - a], Mc, Pc, self.line_id[a])
+                    self._utab[a] = np.ascontiguousarray(utab)                    # host, read by hs2_plan_create
+                    self._d_ucode[a] = torch.from_numpy(ucode).to(dev)
+                    ax.h_utab = self._utab[a].ctypes.data
+                    ax.d_ucode = self._d_ucode[a].data_ptr()
                 if a == 0:
                     M, P = self.chunk[0]
                     self.d_tab_il = torch.from_numpy(interleave_chunks(self.chunk_tabs[0][0], self.shape[2], M, P)).to(dev)

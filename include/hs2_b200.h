@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS2_ABI_VERSION 2
+#define HS2_ABI_VERSION 3
 
 #define HS2_OK 0
 #define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
@@ -61,6 +61,14 @@ extern "C" {
  *                                          chunk p at ((plane*chunk/2 + t)*
  *                                          n_chunks + p)*2; rows past the end
  *                                          of the line hold 1/piv = 1, rest 0
+ *   h_utab [HS2_T_PLANES][chunk]           HOST copy of the most common chunk
+ *                                          table of this axis (may be NULL): the
+ *                                          interior chunks of lines with constant
+ *                                          coefficients are bit-identical; the
+ *                                          kernels receive it by value (constant
+ *                                          bank) and read it without loads
+ *   d_ucode [n_unique][n_chunks] (u8)      1 where chunk p of unique line u
+ *                                          equals h_utab bit for bit, else 0
  * chunk == 0 means the tables are absent and the whole-line path is used.   */
 #define HS2_T_INV 0
 #define HS2_T_F 1
@@ -75,6 +83,8 @@ typedef struct hs2_axis_tables {
   const double *d_tab;
   const double *d_GE;
   const double *d_tab_il;
+  const double *h_utab;      /* HOST pointer, read at launch time, or NULL       */
+  const uint8_t *d_ucode;    /* device, or NULL                                  */
   int32_t n_unique;
   int32_t chunk;
   int32_t n_chunks;
@@ -106,6 +116,8 @@ typedef struct hs2_plan_desc {
 } hs2_plan_desc;
 
 #define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
+#define HS2_FLAG_NO_UTAB 4        /* ignore h_utab / d_ucode (every chunk reads its factor tables) */
+#define HS2_FLAG_X_FOLD 16        /* x sweep: keep the folded LSU-fed kernel even where the TMA-fed one applies */
 
 typedef struct hs2_plan hs2_plan;
 
@@ -123,6 +135,9 @@ typedef struct hs2_source {
 
 int hs2_abi_version(void);
 const char *hs2_last_error(void);
+/* sizeof of the ABI structs as compiled (binding self-check): which = 0 hs2_axis_tables,
+ * 1 hs2_plan_desc, 2 hs2_source; -1 for anything else                         */
+int hs2_sizeof(int which);
 
 /* replaces create_adi_step x3 + finalize (alternatingdirection_c.h:52,
  * alternatingdirection_c_pyx.pyx:212-282)                                     */
@@ -133,9 +148,11 @@ int hs2_plan_destroy(hs2_plan *plan);
 int hs2_plan_launches_per_step(const hs2_plan *plan);
 
 /* which kernel a whole-grid hs2_sweep_x of this plan runs: whole-line
- * global-memory fallback (rhs + Thomas) or the folded tile kernel            */
+ * global-memory fallback (rhs + Thomas), the folded tile kernel or the
+ * TMA-fed patch kernel                                                       */
 #define HS2_XK_WHOLE_LINE 0
 #define HS2_XK_FOLD 1
+#define HS2_XK_TMA 2
 int hs2_plan_x_kernel(const hs2_plan *plan);
 
 /* Which kernel variant the LAST sweep along `axis` (0 = x, 1 = y, 2 = z) of
@@ -151,6 +168,7 @@ int hs2_plan_x_kernel(const hs2_plan *plan);
 #define HS2_K_TILE_CPASYNC_BIG 6
 #define HS2_K_X_FOLD 7         /* sweep_xf_kernel                                        */
 #define HS2_K_Z_SLAB 8         /* z_forward / z_backward of a slab plan                  */
+#define HS2_K_X_TMA 9          /* sweep_xt_kernel: patches staged by TMA, chunk-layout RHS */
 int hs2_plan_last_kernel(const hs2_plan *plan, int axis);
 const char *hs2_kernel_name(int code);
 

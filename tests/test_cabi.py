@@ -27,10 +27,13 @@ def test_library_exports_header_symbols():
 def test_struct_layout_matches_header():
     import ctypes
     from heatsim2_b200 import _cabi
-    # axis tables: 5 pointers + 6 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x4
-    assert ctypes.sizeof(_cabi.AxisTables) == 40 + 24
-    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 64 + 16
+    # axis tables: 7 pointers + 6 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x4
+    assert ctypes.sizeof(_cabi.AxisTables) == 56 + 24
+    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 80 + 16
     assert ctypes.sizeof(_cabi.Source) == 24
+    L = _cabi.lib()
+    for which, struct in enumerate((_cabi.AxisTables, _cabi.PlanDesc, _cabi.Source)):
+        assert L.hs2_sizeof(which) == ctypes.sizeof(struct)
 
 
 def test_argument_validation_without_gpu():

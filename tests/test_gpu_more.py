@@ -137,3 +137,27 @@ def test_slab_kernels_on_one_gpu(hs, name, kwargs, world, nsteps):
     one = util.run_b200(hs, prob, nsteps=nsteps)
     assert util.relerr(got, one) <= 1e-13
     assert util.relerr(got, adi_oracle.run(prob, nsteps=nsteps)) <= 1e-12
+
+
+@pytest.mark.parametrize("name,kwargs", [
+    ("uniform_slab", dict(shape=(96, 128, 160))),
+    ("steelonwater", dict(nz=96, ny=64, nx=128)),
+    ("composite", dict(nz=64, ny=96, nx=128)),
+])
+def test_constant_bank_tables_are_bit_identical(hs, name, kwargs):
+    """uniform-chunk fast path (factors as constant operands, chunk_core.cuh) against the
+    table-load path (HS2_FLAG_NO_UTAB): same values, same operation order -> same bits"""
+    import os
+    prob = problems.ALL[name](hs, **kwargs)
+    old = os.environ.get("HS2_UTAB_AXES")
+    os.environ["HS2_UTAB_AXES"] = "xyz"
+    try:
+        a, plan = _run_plan(hs, prob, 3, flags=0)
+        b, _ = _run_plan(hs, prob, 3, flags=4)        # HS2_FLAG_NO_UTAB
+    finally:
+        if old is None:
+            del os.environ["HS2_UTAB_AXES"]
+        else:
+            os.environ["HS2_UTAB_AXES"] = old
+    assert all(u is not None and int(u.sum()) > 0 for u in plan._d_ucode), "no uniform chunks found"
+    assert np.array_equal(a, b)

@@ -49,14 +49,16 @@ def _steps_vs_oracle(hs, prob, nsteps, restart=True):
 
 # (problem, kwargs, long axis 0=x 1=y 2=z, expected (chunk rows, chunks) on it, expected kernel on it)
 LONG_LINES = [
-    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (32, 16), "x-fold"),
+    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (16, 32), "x-tma"),
     ("uniform_slab", dict(shape=(8, 512, 16)), 1, (32, 16), "tile-tma"),
     ("uniform_slab", dict(shape=(512, 8, 16)), 2, (32, 16), "tile-cpasync"),
     ("uniform_slab", dict(shape=(8, 16, 1024)), 0, (32, 32), "x-fold"),
     ("uniform_slab", dict(shape=(8, 1024, 16)), 1, (32, 32), "tile-tma-512"),
     ("uniform_slab", dict(shape=(1024, 8, 16)), 2, (32, 32), "tile-cpasync-512"),
     # several unique lines along the long axis (material change, thin layer, delamination)
-    ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (32, 16), "x-fold"),
+    ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (16, 32), "x-tma"),
+    ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-tma"),      # odd plane count, ragged row patches
+    ("composite", dict(nz=19, ny=10, nx=256), 0, (16, 16), "x-tma"),
     ("steelonwater", dict(nz=8, ny=512, nx=16), 1, (32, 16), "tile-tma"),
     ("composite", dict(nz=512, ny=8, nx=16), 2, (32, 16), "tile-cpasync"),
     ("composite", dict(nz=1024, ny=8, nx=16), 2, (32, 32), "tile-cpasync-512"),
@@ -65,6 +67,19 @@ LONG_LINES = [
     ("uniform_slab", dict(shape=(4, 512, 512)), 1, (32, 16), "tile-tma"),
     ("uniform_slab", dict(shape=(512, 4, 512)), 2, (32, 16), "tile-cpasync"),
 ]
+
+
+# the LSU-fed folded x kernel (kernels_xf.cu) stays the path of lines the TMA kernel does not take; forced here at 512
+FOLD_LINES = [
+    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (32, 16), "x-fold"),
+    ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (32, 16), "x-fold"),
+]
+
+
+@pytest.mark.parametrize("name,kwargs,axis,chunk,kernel", FOLD_LINES)
+def test_folded_x_kernel_vs_oracle(hs, monkeypatch, name, kwargs, axis, chunk, kernel):
+    monkeypatch.setenv("HS2_X_KERNEL", "fold")
+    test_long_lines_vs_oracle(hs, name, kwargs, axis, chunk, kernel)
 
 
 @pytest.mark.parametrize("name,kwargs,axis,chunk,kernel", LONG_LINES)
@@ -122,7 +137,7 @@ def test_survey_sizes_vs_reference_digests(hs, case):
     if cols:
         got = torch.stack(hist).cpu().numpy()
         assert util.relerr(got, z["surface_hist"]) <= TOL_RUN
-    assert all(k.startswith("tile") or k == "x-fold" for k in P.plan.last_kernels()), P.plan.last_kernels()
+    assert all(k.startswith("tile") or k == "x-tma" for k in P.plan.last_kernels()), P.plan.last_kernels()
 
 
 def test_c2_64_1000_steps_vs_oracle(hs):
