@@ -57,9 +57,30 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
-// 32-byte store (one full sector per lane)
-__device__ __forceinline__ void stg256(double *p, double a, double b, double c, double d) {
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+template <typename CID>
+__device__ __forceinline__ int xt_cell_class(const uint32_t *idw, int e) {
+  return sizeof(CID) == 1 ? (int)((idw[e >> 2] >> (8 * (e & 3))) & 0xff) : (int)((idw[e >> 1] >> (16 * (e & 1))) & 0xffff);
+}
+
+// all 16 cells of the chunk in one equation class?
+template <typename CID>
+__device__ __forceinline__ bool xt_one_class(const uint32_t *idw) {
+  if (sizeof(CID) == 1) {
+    const uint32_t pat = (idw[0] & 0xffu) * 0x01010101u;
+    return idw[0] == pat && idw[1] == pat && idw[2] == pat && idw[3] == pat;
+  }
+  const uint32_t pat = (idw[0] & 0xffffu) * 0x00010001u;
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) ok = ok && idw[q] == pat;
+  return ok;
 }
 
 struct XtMaps {
@@ -67,6 +88,7 @@ struct XtMaps {
   CUtensorMap Z;     // T: box (16, 4, 1, S)   one plane, the patch rows
   CUtensorMap Hlo;   // halo_lo plane (nz = 1): box (16, 4, 1, S); unused when no halo
   CUtensorMap Hhi;   // halo_hi plane
+  CUtensorMap O;     // work: box (16, 4, 1, S)
 };
 
 // patch index -> (range, first plane, first row)
@@ -180,32 +202,55 @@ sweep_xt_kernel(const __grid_constant__ XtMaps tm, const __grid_constant__ UTab 
   const unsigned char *rowB = (pz == 0 ? sZL : sZH) + lz * 128;
   const int kB = lz & 7;
 
+  // class ids of the thread's 16 cells and the unique-line id of its line are fetched ONE PATCH AHEAD (plain
+  // global loads that stay in flight during a whole patch), so that nothing waits for them
+  constexpr int NIDW = sizeof(CID) == 1 ? 4 : 8;
+  auto fetch_ids = [&](int rr, int kk0, int jj0, uint32_t (&ids)[NIDW], uint32_t &lid_out) {
+    const int kq = kk0 + pz, jq = jj0 + rw;
+    lid_out = 0;
+    if (active && jq < ny && kq < rg.k1[rr]) {
+      const uint4 *q4 = reinterpret_cast<const uint4 *>(cid + ((int64_t)kq * plane + (int64_t)jq * nx + p * XT_M));
+      const uint4 a = __ldg(q4);
+      ids[0] = a.x, ids[1] = a.y, ids[2] = a.z, ids[3] = a.w;
+      if (sizeof(CID) == 2) {
+        const uint4 b = __ldg(q4 + 1);
+        ids[NIDW - 4] = b.x, ids[NIDW - 3] = b.y, ids[NIDW - 2] = b.z, ids[NIDW - 1] = b.w;
+      }
+      lid_out = __ldg(line_id + (int64_t)kq * ny + jq);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NIDW; ++q) ids[q] = 0;
+    }
+  };
+  int r = 0, k0 = 0, j0 = 0;
+  uint32_t idw[NIDW], idn[NIDW];
+  uint32_t lid = 0, lidn = 0;
+  if (t < n_tiles) {
+    xt_decode(t, rg, tiles_y, &r, &k0, &j0);
+    fetch_ids(r, k0, j0, idw, lid);
+  }
+  bool first = true;
   HS2_MARK_DECL;
   for (; t < n_tiles; t += gridDim.x) {
-    int r, k0, j0;
-    xt_decode(t, rg, tiles_y, &r, &k0, &j0);
     const int k = k0 + pz, j = j0 + rw;
     const bool line_ok = active && j < ny && k < rg.k1[r];     // this thread's line exists and belongs to the launch
     const int64_t cell0 = (int64_t)k * plane + (int64_t)j * nx + p * XT_M;
-    // class ids of the 16 cells and the unique-line id: requested before the wait on the copy engine
-    uint32_t idw[sizeof(CID) == 1 ? 4 : 8];
-    uint32_t lid = 0;
-    if (line_ok) {
-      const uint4 *q4 = reinterpret_cast<const uint4 *>(cid + cell0);
-      const uint4 a = __ldg(q4);
-      idw[0] = a.x, idw[1] = a.y, idw[2] = a.z, idw[3] = a.w;
-      if (sizeof(CID) == 2) {
-        const uint4 b = __ldg(q4 + 1);
-        idw[4] = b.x, idw[5] = b.y, idw[6] = b.z, idw[7] = b.w;
-      }
-      lid = __ldg(line_id + (int64_t)k * ny + j);
-    } else {
-#pragma unroll
-      for (int q = 0; q < (sizeof(CID) == 1 ? 4 : 8); ++q) idw[q] = 0;
+    const bool more = t + (int)gridDim.x < n_tiles;
+    int rn = 0, tn_k0 = 0, tn_j0 = 0;
+    if (more) {
+      xt_decode(t + gridDim.x, rg, tiles_y, &rn, &tn_k0, &tn_j0);
+      fetch_ids(rn, tn_k0, tn_j0, idn, lidn);
     }
     // last plane of an odd plane count: the upper plane of the patch does not exist and the lower plane's z+
     // neighbour (the plane above the grid) sits in ZH -> both z streams are "late"
     const bool lone = k0 + 1 >= nz;
+    if (tid == 0 && !first) {
+      // the previous patch's d1 left through the Z buffers: once the copy engine has read them, fetch this
+      // patch's lower / upper plane rows into them (they are consumed last, below)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_Z(k0, j0);
+    }
+    first = false;
     HS2_MARK(0);
     mbar_wait(bar, parity);
     if (lone) mbar_wait(bar + 1, parity);
@@ -215,6 +260,11 @@ sweep_xt_kernel(const __grid_constant__ XtMaps tm, const __grid_constant__ UTab 
     double v[XT_M];
     uint8_t uc = 1;
     if (TABSRC >= 1 && ucode != nullptr && active) uc = __ldg(ucode + (int64_t)lid * P + p);   // used after the stencil
+    // common case, decided per warp: no source term and every chunk of the warp lies in one equation class ->
+    // straight-line code (no per-cell class test), so that the 16 cells' dependency chains interleave
+    const bool plain = !has_src && __all_sync(0xffffffffu, xt_one_class<CID>(idw));
+    const unsigned char *rA = (lone && pz == 0) ? sZH + lz * 128 : rowA;
+    const int keyA = (lone && pz == 0) ? kB : kA;
     if (active) {
       // centre values first: they are also the x neighbours
 #pragma unroll
@@ -226,52 +276,75 @@ sweep_xt_kernel(const __grid_constant__ XtMaps tm, const __grid_constant__ UTab 
       // x neighbours across the chunk ends (closed outer faces: conductance 0, any finite value)
       double xl = p > 0 ? *reinterpret_cast<const double *>(rowC - 12 * 128 + (((7 ^ ((lc - 12) & 7)) << 4) + 8)) : v[0];
       const double xr_end = p < P - 1 ? *reinterpret_cast<const double *>(rowC + 12 * 128 + (((lc + 12) & 7) << 4)) : v[XT_M - 1];
-      const unsigned char *rA = (lone && pz == 0) ? sZH + lz * 128 : rowA;
-      const int keyA = (lone && pz == 0) ? kB : kA;
-      int last_id = -1;
-      double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0, csrc = 0;
+      if (plain) {
+        const double2 *c2 = reinterpret_cast<const double2 *>(coef + xt_cell_class<CID>(idw, 0) * HS2_COEF_STRIDE);
+        const double2 a0 = c2[0], a1 = c2[1], a2 = c2[2];
+        const double cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+        const double cA = pz == 0 ? a2.y : a2.x, cB = pz == 0 ? a2.x : a2.y;
+        const double csum = -(((cxm + cxp) + (cym + cyp)) + (cA + cB));
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double2 ym = *reinterpret_cast<const double2 *>(rowYm + ((u ^ kYm) << 4));
-        const double2 yp = *reinterpret_cast<const double2 *>(rowYp + ((u ^ kYp) << 4));
-        const double2 za = *reinterpret_cast<const double2 *>(rA + ((u ^ keyA) << 4));
+        for (int u = 0; u < 8; ++u) {
+          const double2 ym = *reinterpret_cast<const double2 *>(rowYm + ((u ^ kYm) << 4));
+          const double2 yp = *reinterpret_cast<const double2 *>(rowYp + ((u ^ kYp) << 4));
+          const double2 za = *reinterpret_cast<const double2 *>(rA + ((u ^ keyA) << 4));
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int e = 2 * u + c;
-          int idc;
-          if (sizeof(CID) == 1)
-            idc = (idw[e >> 2] >> (8 * (e & 3))) & 0xff;
-          else
-            idc = (idw[e >> 1] >> (16 * (e & 1))) & 0xffff;
-          if (idc != last_id) {   // cells of one material share a class: usually taken once per chunk
-            const double2 *c2 = reinterpret_cast<const double2 *>(coef + idc * HS2_COEF_STRIDE);
-            const double2 a0 = c2[0], a1 = c2[1], a2 = c2[2];
-            cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
-            cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
-            cB = pz == 0 ? a2.x : a2.y;
-            csrc = c2[3].x;
-            last_id = idc;
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const double tt = v[e];
+            const double xr = e < XT_M - 1 ? v[e + 1] : xr_end;
+            double rr = cxm * (xl - tt);
+            rr = fma(cxp, xr - tt, rr);
+            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
+            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
+            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
+            rr = fma(-cB, tt, rr);             // the late stream adds cB * z below
+            xl = tt;
+            v[e] = rr;
           }
-          const double tt = v[e];
-          const double xr = e < XT_M - 1 ? v[e + 1] : xr_end;
-          double rr = cxm * (xl - tt);
-          rr = fma(cxp, xr - tt, rr);
-          rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
-          rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
-          rr = fma(cA, (c ? za.y : za.x) - tt, rr);
-          rr = fma(-cB, tt, rr);             // the late stream adds cB * z below
-          if (has_src && line_ok) {
-            double sv = dense ? dense[cell0 + e] : 0.0;
-            if (st.n) {
-              const uint8_t vv = vol[cell0 + e];
+        }
+        (void)csum;
+      } else {
+        int last_id = -1;
+        double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0, csrc = 0;
 #pragma unroll
-              for (int s = 0; s < 8; ++s)
-                if (s < st.n && st.idx[s] == vv) sv += st.val[s];
+        for (int u = 0; u < 8; ++u) {
+          const double2 ym = *reinterpret_cast<const double2 *>(rowYm + ((u ^ kYm) << 4));
+          const double2 yp = *reinterpret_cast<const double2 *>(rowYp + ((u ^ kYp) << 4));
+          const double2 za = *reinterpret_cast<const double2 *>(rA + ((u ^ keyA) << 4));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int idc = xt_cell_class<CID>(idw, e);
+            if (idc != last_id) {
+              const double2 *c2 = reinterpret_cast<const double2 *>(coef + idc * HS2_COEF_STRIDE);
+              const double2 a0 = c2[0], a1 = c2[1], a2 = c2[2];
+              cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+              cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
+              cB = pz == 0 ? a2.x : a2.y;
+              csrc = c2[3].x;
+              last_id = idc;
             }
-            rr = fma(csrc, sv, rr);
+            const double tt = v[e];
+            const double xr = e < XT_M - 1 ? v[e + 1] : xr_end;
+            double rr = cxm * (xl - tt);
+            rr = fma(cxp, xr - tt, rr);
+            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
+            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
+            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
+            rr = fma(-cB, tt, rr);
+            if (has_src && line_ok) {
+              double sv = dense ? dense[cell0 + e] : 0.0;
+              if (st.n) {
+                const uint8_t vv = vol[cell0 + e];
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                  if (s < st.n && st.idx[s] == vv) sv += st.val[s];
+              }
+              rr = fma(csrc, sv, rr);
+            }
+            xl = tt;
+            v[e] = rr;
           }
-          xl = tt;
-          v[e] = rr;
         }
       }
     } else {
@@ -281,41 +354,39 @@ sweep_xt_kernel(const __grid_constant__ XtMaps tm, const __grid_constant__ UTab 
     if (!lone) mbar_wait(bar + 1, parity);
     parity ^= 1;
     if (active) {
-      const unsigned char *rB = rowB;
-      int last_id = -1;
-      double cB = 0;
+      if (plain) {
+        const double2 a2 = reinterpret_cast<const double2 *>(coef + xt_cell_class<CID>(idw, 0) * HS2_COEF_STRIDE)[2];
+        const double cB = pz == 0 ? a2.x : a2.y;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double2 zb = *reinterpret_cast<const double2 *>(rB + ((u ^ kB) << 4));
+        for (int u = 0; u < 8; ++u) {
+          const double2 zb = *reinterpret_cast<const double2 *>(rowB + ((u ^ kB) << 4));
+          v[2 * u] = fma(cB, zb.x, v[2 * u]);
+          v[2 * u + 1] = fma(cB, zb.y, v[2 * u + 1]);
+        }
+      } else {
+        int last_id = -1;
+        double cB = 0;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int e = 2 * u + c;
-          int idc;
-          if (sizeof(CID) == 1)
-            idc = (idw[e >> 2] >> (8 * (e & 3))) & 0xff;
-          else
-            idc = (idw[e >> 1] >> (16 * (e & 1))) & 0xffff;
-          if (idc != last_id) {
-            const double2 a2 = reinterpret_cast<const double2 *>(coef + idc * HS2_COEF_STRIDE)[2];
-            cB = pz == 0 ? a2.x : a2.y;
-            last_id = idc;
+        for (int u = 0; u < 8; ++u) {
+          const double2 zb = *reinterpret_cast<const double2 *>(rowB + ((u ^ kB) << 4));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int idc = xt_cell_class<CID>(idw, e);
+            if (idc != last_id) {
+              const double2 a2 = reinterpret_cast<const double2 *>(coef + idc * HS2_COEF_STRIDE)[2];
+              cB = pz == 0 ? a2.x : a2.y;
+              last_id = idc;
+            }
+            v[e] = fma(cB, c ? zb.y : zb.x, v[e]);
           }
-          v[e] = fma(cB, c ? zb.y : zb.x, v[e]);
         }
       }
     }
     HS2_MARK(2);
     __syncthreads();     // the stage has been read
     HS2_MARK(3);
-    int tn_k0 = 0, tn_j0 = 0;
-    const bool more = t + (int)gridDim.x < n_tiles;
-    (void)tn_k0, (void)tn_j0;
-    if (tid == 0 && more) {
-      int rn;
-      xt_decode(t + gridDim.x, rg, tiles_y, &rn, &tn_k0, &tn_j0);
-      issue_C(tn_k0, tn_j0);      // both travel during the solve
-      issue_Z(tn_k0, tn_j0);
-    }
+    if (tid == 0 && more) issue_C(tn_k0, tn_j0);      // travels during the solve
 
     // ------------------------------------------------ partitioned solve along x (chunk_core.cuh)
     const int pcl = active ? p : 0;
@@ -385,15 +456,26 @@ sweep_xt_kernel(const __grid_constant__ XtMaps tm, const __grid_constant__ UTab 
       chunk_backward_full<XT_M>(v, tb, tpitch, alpha, E);
 
     HS2_MARK(8);
-    // ------------------------------------------------ d1 straight from registers: the thread's 16 cells are one
-    // 128-byte line of the output, written as four 32-byte sectors (st.global.v4.f64, sm_100)
-    if (line_ok) {
-      double *o = Wout + cell0;
+    // ------------------------------------------------ d1 -> the dead Z buffers (same swizzle) -> bulk tensor store
+    if (active) {
+      unsigned char *o = (pz == 0 ? sZL : sZH) + lz * 128;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) stg256(o + 4 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+      for (int u = 0; u < 8; ++u) *reinterpret_cast<double2 *>(o + ((u ^ kB) << 4)) = make_double2(v[2 * u], v[2 * u + 1]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_4d(&tm.O, sZL, 0, j0, k0, 0);
+      if (k0 + 1 < rg.k1[r]) tma_store_4d(&tm.O, sZH, 0, j0, k0 + 1, 0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     HS2_MARK(9);
+    r = rn, k0 = tn_k0, j0 = tn_j0;
+    lid = lidn;
+#pragma unroll
+    for (int q = 0; q < NIDW; ++q) idw[q] = idn[q];
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 bool encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int rows, int planes) {
@@ -446,8 +528,8 @@ int launch_xt(hs2_plan *p, const double *T, double *W, const hs2_source *src, co
   if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
   XtMaps tm;
   memset(&tm, 0, sizeof(tm));
-  if (!encode4(&tm.C, T, nx, ny, nz, 6, 2) || !encode4(&tm.Z, T, nx, ny, nz, 4, 1)) return HS2_OK;
-  if (reinterpret_cast<uintptr_t>(W) & 31) return HS2_OK;      // 32-byte vector stores
+  if (!encode4(&tm.C, T, nx, ny, nz, 6, 2) || !encode4(&tm.Z, T, nx, ny, nz, 4, 1) || !encode4(&tm.O, W, nx, ny, nz, 4, 1))
+    return HS2_OK;
   if (halo_lo && !encode4(&tm.Hlo, halo_lo, nx, ny, 1, 4, 1)) return HS2_OK;
   if (halo_hi && !encode4(&tm.Hhi, halo_hi, nx, ny, 1, 4, 1)) return HS2_OK;
   const uint32_t szC = round1k((uint32_t)P * 12 * 128), szZ = round1k((uint32_t)P * 4 * 128);
