@@ -3,6 +3,12 @@
 end-to-end and CPU-baseline figures, as ONE JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--impl b200|reference]
+                    [--workload uniform|c2_256|c3_steelonwater_512|c4_composite_256x512x512] [--scaling weak|strong]
+
+--workload (N=1) runs the other BASELINE.json configurations with their real geometries (tests/problems.py):
+c2_256 = configs[1] as written (256^3, 1000 steps), c3 = demos/steelonwater.py geometry at 512^3 with thin
+insulating layers, c4 = anisotropic composite 256x512x512 with delamination and the z-min surface temperature
+evaluated on the device tensor after every step (inside the timed region).
 
 Workload (BASELINE.json configs[1] recipe at north_star's target size):
 uniform isotropic steel slab, insulating outer faces, conducting interior,
@@ -103,13 +109,22 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------- CPU baselines
-def _ref_replica(grid, steps, warmup, conn):
+def sample_problem(hs, workload, grid):
+    """the bench workload's recipe on a grid the CPU reference can hold (1.5 kB of host RAM per cell)"""
+    import problems
+    if workload.startswith("c3"):
+        return problems.steelonwater(hs, nz=grid, ny=grid, nx=grid)
+    if workload.startswith("c4"):
+        return problems.composite(hs, nz=grid // 2, ny=grid, nx=grid, ply=8)
+    return problems.uniform_slab(hs, n=grid)
+
+
+def _ref_replica(grid, steps, warmup, conn, workload="uniform"):
     """one process: the unmodified reference on a grid^3 sample of the workload"""
     import numpy as np
-    import problems
     import ref_loader
     ref = ref_loader.load()
-    prob = problems.uniform_slab(ref, n=grid)
+    prob = sample_problem(ref, workload, grid)
     t0 = time.perf_counter()
     P, S = ref_loader.quiet_setup(ref, *prob["setup_args"])
     t_setup = time.perf_counter() - t0
@@ -127,15 +142,15 @@ def _ref_replica(grid, steps, warmup, conn):
     conn.send(("done", time.perf_counter() - t0))
 
 
-def time_reference(grid, steps, warmup, replicas):
+def time_reference(grid, steps, warmup, replicas, workload="uniform"):
     """Reference Cython/C path (oracle/_ref) on `replicas` host processes, each
-    stepping its own grid^3 uniform slab.  Returns cells/s (aggregate), secs."""
+    stepping its own sample of the workload.  Returns cells/s (aggregate), secs, setup secs."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     procs = []
     for _ in range(replicas):
         a, b = ctx.Pipe()
-        pr = ctx.Process(target=_ref_replica, args=(grid, steps, warmup, b))
+        pr = ctx.Process(target=_ref_replica, args=(grid, steps, warmup, b, workload))
         pr.start()
         procs.append((pr, a))
     setups = [a.recv()[1] for _, a in procs]
@@ -144,16 +159,16 @@ def time_reference(grid, steps, warmup, replicas):
     times = [a.recv()[1] for _, a in procs]
     for pr, _ in procs:
         pr.join()
-    cells = replicas * steps * grid ** 3
+    per = grid ** 3 // 2 if workload.startswith("c4") else grid ** 3
+    cells = replicas * steps * per
     return cells / max(times), max(times), max(setups)
 
 
-def time_oracle_port(grid, steps, warmup):
+def time_oracle_port(grid, steps, warmup, workload="uniform"):
     import numpy as np
     import adi_oracle
-    import problems
     import heatsim2_b200 as hs
-    prob = problems.uniform_slab(hs, n=grid)
+    prob = sample_problem(hs, workload, grid)
     O = adi_oracle.setup(*prob["setup_args"])
     T = np.array(prob["T0"])
     for it in range(warmup):
@@ -162,20 +177,23 @@ def time_oracle_port(grid, steps, warmup):
     for it in range(steps):
         T = O.step(prob["dt"] * (warmup + it), prob["dt"], T)
     el = time.perf_counter() - t0
-    return steps * grid ** 3 / el, el
+    return steps * int(np.prod(prob["shape"])) / el, el
 
 
-def cpu_baseline(sample_grid=64, steps=20, warmup=2):
+def cpu_baseline(workload="uniform", sample_grid=128, steps=20, warmup=1):
+    """The reference on ONE host core (it is single-threaded) at 128^3 - the largest grid it builds in reasonable
+    time and memory (3.2 GB, 37 s of setup; 256^3 needs 26 GB and 5 min) - about 10 s of timed CPU work."""
     import ref_loader
     if ref_loader.available():
-        v, el, su = time_reference(sample_grid, steps, warmup, 1)
+        v, el, su = time_reference(sample_grid, steps, warmup, 1, workload)
         return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": "unmodified reference (oracle/_ref) run_adi_steps, %d steps of the same recipe at %d^3 "
-                          "(larger grids need 1.5 kB/cell of host RAM); setup %.1f s not timed" % (steps, sample_grid, su),
-                "host_cpus": os.cpu_count()}
-    v, el = time_oracle_port(sample_grid, steps, warmup)
+                "sample": "unmodified reference (oracle/_ref) run_adi_steps, %d steps of the workload's recipe on a %d-cell-wide "
+                          "sample (the largest the reference builds in reasonable time: 1.5 kB of host RAM and 17 us of setup "
+                          "per cell); setup %.1f s not timed" % (steps, sample_grid, su),
+                "sample_grid": sample_grid, "host_cpus": os.cpu_count()}
+    v, el = time_oracle_port(min(sample_grid, 64), steps, warmup, workload)
     return {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "numpy oracle, %d steps at %d^3" % (steps, sample_grid), "host_cpus": os.cpu_count()}
+            "sample": "numpy oracle, %d steps at %d cells wide" % (steps, min(sample_grid, 64)), "host_cpus": os.cpu_count()}
 
 
 def run_reference_arm(args):
@@ -183,17 +201,20 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import ref_loader
-    grid = 64
+    # all host cores: one single-threaded replica per core (the reference has no threading), each on the largest
+    # sample that leaves every replica its 1.5 kB per cell: 96^3 = 1.4 GB per replica
+    grid = int(os.environ.get("HS2_REF_GRID", "96"))
     if ref_loader.available():
         replicas = max(1, min(os.cpu_count() or 1, 32))
-        v, el, su = time_reference(grid, args.steps, args.warmup, replicas)
+        v, el, su = time_reference(grid, args.steps, args.warmup, replicas, args.workload)
         kind, cores = "reference", replicas
         sample = ("unmodified reference (oracle/_ref), %d independent single-threaded replicas (the reference has no "
-                  "threading), each %d steps of the workload recipe at %d^3" % (replicas, args.steps, grid))
+                  "threading), each %d steps of the workload recipe on a %d-cell-wide sample (1.4 GB of matrices per replica; "
+                  "the full grid would need %.0f GB)" % (replicas, args.steps, grid, 1.5e3 * 512 ** 3 / 1e9))
     else:
-        v, el = time_oracle_port(grid, args.steps, args.warmup)
+        v, el = time_oracle_port(min(grid, 64), args.steps, args.warmup, args.workload)
         kind, cores = "port", 1
-        sample = "numpy oracle port, %d steps at %d^3" % (args.steps, grid)
+        sample = "numpy oracle port, %d steps at %d cells wide" % (args.steps, min(grid, 64))
     shape = grid_for(args.gpus, args.grid, args.scaling)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -223,8 +244,35 @@ def run_b200_single(args):
     shape = grid_for(1, args.grid, args.scaling)
     if args.shape:
         shape = tuple(int(v) for v in args.shape.split(","))
+    surface_each_step = False
+    if args.workload == "c2_256":
+        shape = (256, 256, 256)
+        if not args.steps_given:
+            args.steps = 1000
+    if args.workload in ("uniform", "c2_256"):
+        prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
+        wname = workload_name(shape) if args.workload == "uniform" else \
+            "BASELINE configs[1] as written: uniform isotropic steel slab 256^3, insulating faces, %d ADI steps" % args.steps
+    elif args.workload == "c3_steelonwater_512":
+        g = args.grid
+        shape = (g, g, g)
+        prob = problems.steelonwater(hs, nz=g, ny=g, nx=g)
+        prob["T0"] = None
+        wname = ("BASELINE configs[2]: demos/steelonwater.py geometry at %d^3 (water pocket, FIXED last layer, insulated faces, "
+                 "dt=0.05) with boundary_thininsulatinglayer h=1000 W/m^2K on every steel/water face" % g)
+    elif args.workload == "c4_composite_256x512x512":
+        g = args.grid
+        shape = (g // 2, g, g)
+        prob = problems.composite(hs, nz=g // 2, ny=g, nx=g, ply=8)
+        prob["T0"] = None
+        surface_each_step = True
+        wname = ("BASELINE configs[3]: anisotropic composite %dx%dx%d (z,y,x), plies diag(0.71,0.71,5.1)/diag(0.71,5.1,0.71) "
+                 "every 8 layers, boundary_conducting_anisotropic, rectangular delamination, "
+                 "surface_temperature.insulating_z_min_surface_temperature on the device tensor after EVERY step "
+                 "(inside the timed region)" % shape)
+    else:
+        raise SystemExit("unknown workload %r" % args.workload)
     t0 = time.perf_counter()
-    prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
     P, S = hs.setup(*prob["setup_args"])
     plan = P.plan
     plan.ensure_device(dev)
@@ -233,6 +281,8 @@ def run_b200_single(args):
     rng = np.random.default_rng(1234)
     T_host = torch.empty(shape, dtype=torch.float64).pin_memory()
     T_host.numpy()[...] = rng.random(shape)
+    if args.workload.startswith("c3"):
+        T_host.numpy()[prob["material_elements"] == 2] = 0.0          # TEMPERATURE_FIXED sink layer held at 0
     Ta = T_host.to(dev)
     Tb = torch.empty_like(Ta)
     dt = prob["dt"]
@@ -254,16 +304,21 @@ def run_b200_single(args):
     torch.cuda.synchronize()
     tb = time.time()
     e0.record()
+    surf_acc = None
     for _ in range(args.steps):
         hs.run_adi_steps(P, S, it * dt, dt, Ta, ve, vol, out=Tb)
         Ta, Tb = Tb, Ta
         it += 1
+        if surface_each_step:
+            surf = hs.surface_temperature.insulating_z_min_surface_temperature(Ta, prob["dz"])
+            surf_acc = surf if surf_acc is None else surf_acc.add_(surf)
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     # ---- per-kernel: same steps as three C-ABI calls with events between them
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    for k in range(args.steps):
+    n_k = min(args.steps, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_k)]
+    for k in range(n_k):
         plan.timed_sweeps(Ta, Tb, evs[k])
         Ta, Tb = Tb, Ta
     torch.cuda.synchronize()
@@ -271,7 +326,7 @@ def run_b200_single(args):
     clocks = sampler.stop(tb, te)
     sweep_ms = {}
     for si, name in enumerate("xyz"):
-        sweep_ms[name] = sum(e[si].elapsed_time(e[si + 1]) for e in evs) / args.steps
+        sweep_ms[name] = sum(e[si].elapsed_time(e[si + 1]) for e in evs) / n_k
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
     peaks = {}
@@ -285,19 +340,42 @@ def run_b200_single(args):
     kernels = {k: {"ms": sweep_ms[k], "algorithmic_bytes": BYTES_PER_CELL[k] * n,
                    "GBps": BYTES_PER_CELL[k] * n / (sweep_ms[k] * 1e-3) / 1e9,
                    "frac": BYTES_PER_CELL[k] * n / (sweep_ms[k] * 1e-3) / 1e9 / peak} for k in sweep_ms}
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel: NOT measured in this run (that needs ncu); imported from the
+    # committed ncu --set full capture of the same kernel at 512^3 and scaled by the cell count
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        tj = json.load(open(tpath))
+        if dom in tj:
+            traffic = tj[dom] * n / float(tj.get("cells", 512 ** 3))
+            traffic_src = "imported: %s (ncu dram__bytes_read+write.sum at %d cells, scaled to %d)" % (
+                tj.get("source", "profiles/traffic.json"), int(tj.get("cells", 512 ** 3)), n)
     roofline = {"bound": "hbm", "kernel": "sweep_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "step": {"algorithmic_bytes": 56 * n, "GBps": 56 * n / (ms_step * 1e-3) / 1e9,
                          "frac": 56 * n / (ms_step * 1e-3) / 1e9 / peak, "frac_of_8TBps_nominal": 56 * n / (ms_step * 1e-3) / 8e12},
                 "kernels": kernels}
-    # ---- e2e: host buffers in and out of run_adi_steps every step (pinned)
+    # ---- e2e: the reference's own contract - numpy array in, new numpy array out of run_adi_steps, every step
+    # (alternatingdirection_c_pyx.pyx:287,416); wall clock, because the host-side staging copies are part of it
+    e2e_steps = max(3, min(args.steps, 10))
+    A = T_host.numpy().copy()
+    for _ in range(2):
+        A = hs.run_adi_steps(P, S, it * dt, dt, A, ve, vol)
+    torch.cuda.synchronize()
+    t0w = time.perf_counter()
+    for _ in range(e2e_steps):
+        A = hs.run_adi_steps(P, S, it * dt, dt, A, ve, vol)
+        it += 1
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0w) * 1e3 / e2e_steps
+    assert isinstance(A, np.ndarray) and bool(np.isfinite(A[::7, ::5, ::3]).all())
+    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+           "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "heatsim2_b200.run_adi_steps(numpy float64 array in -> new numpy array out), the reference's call; "
+                  "pageable user arrays are staged through pinned buffers in pipelined chunks"}
+    # the same round trip with caller-pinned host tensors (no staging copies): what PCIe alone costs
     H_in = T_host
     H_out = torch.empty(shape, dtype=torch.float64).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         hs.run_adi_steps(P, S, it * dt, dt, H_in, ve, vol, out=H_out)
         H_in, H_out = H_out, H_in
@@ -309,10 +387,9 @@ def run_b200_single(args):
         it += 1
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
-           "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "api": "heatsim2_b200.run_adi_steps(host float64 tensor [pinned] -> host tensor)"}
+    pin_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_pinned = {"value": n / (pin_ms * 1e-3), "unit": UNIT, "ms_per_step": pin_ms, "steps": e2e_steps,
+                  "api": "heatsim2_b200.run_adi_steps(pinned host float64 tensor -> pinned host tensor, out=)"}
     assert bool(torch.isfinite(Ta).all())
     # ---- same host-in / host-out contract, but through the multi-step call a device-resident user makes
     # (run_adi_steps_n: one upload, N steps with two probes recorded on the device, one download); context
@@ -320,7 +397,7 @@ def run_b200_single(args):
     e2e_resident = None
     try:
         n_res = 50
-        h_np = H_in.numpy()
+        h_np = A
         torch.cuda.synchronize()
         t0w = time.perf_counter()
         T_fin, rec = hs.run_adi_steps_n(P, S, it * dt, dt, h_np, ve, vol, n_res, probes=[(0, 1, 1), (shape[0] // 2, 2, 3)])
@@ -332,15 +409,16 @@ def run_b200_single(args):
         del T_fin, rec
     except Exception as exc:          # informational figure: never let it take the bench line down
         e2e_resident = {"error": str(exc)[:200]}
-    base = cpu_baseline() if not args.no_cpu_baseline else None
+    base = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(shape), "grid": list(shape), "cells": n,
+            "config": {"workload": wname, "grid": list(shape), "cells": n,
                        "l2": "inputs larger than L2 (3 arrays of %.2f GB vs 126 MB)" % (n * 8 / 1e9),
                        "classes": plan.n_classes, "unique_lines": list(plan.n_unique), "setup_s": setup_s,
-                       "x_kernel": plan.x_kernel},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "e2e_resident": e2e_resident,
+                       "x_kernel": plan.x_kernel, "kernels": list(plan.last_kernels()),
+                       "surface_temperature_each_step": surface_each_step},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "e2e_pinned": e2e_pinned, "e2e_resident": e2e_resident,
             "gpu_launches": args.steps * plan.launches_per_step, "clocks": clocks}
     print(json.dumps(line))
 
@@ -348,7 +426,7 @@ def run_b200_single(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -357,7 +435,12 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: grid^3 cells per GPU (default, the driver's SCALE run); strong: (2*grid)^3 = 1024^3 "
                          "on every GPU count (BASELINE configs[4])")
+    ap.add_argument("--workload", default="uniform",
+                    choices=["uniform", "c2_256", "c3_steelonwater_512", "c4_composite_256x512x512"])
     args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 50
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.gpus == 1:

@@ -50,6 +50,17 @@ class pyadi_step(object):
         self.permutedshape = [ADI_params.shape[a] for a in permuteorder]
         self.invpermuteorder = tuple(int(a) for a in np.argsort(permuteorder))
 
+    def add_equation(self, posindex, eqdict):
+        """Reference method (:177-209): the equation ``{variable name: coefficient}`` of THIS stage for cell
+        ``posindex = (k, j, i)``.  The reference hands it to C ``add_equation``, which appends COO triplets; here it
+        is recorded, and once a cell has its equation for all three stages the cell joins an equation class of the
+        plan builder (same rules, ``parse_stage_dict``).  ``finalize()`` of any stage then compiles the plan."""
+        builder = getattr(self.ADI_params, "_cell_builder", None)
+        if builder is None:
+            from .plan import CellwiseBuilder
+            builder = self.ADI_params._cell_builder = CellwiseBuilder(self.ADI_params.shape)
+        builder.add_stage(self.stepnum, tuple(int(v) for v in posindex), dict(eqdict))
+
     def finalize(self):
         """The reference converts COO->CSR and LU-factors here (:212-282).
         Plans made by setup() are complete already; when equations were added

@@ -60,7 +60,7 @@ def _operand(name):
     return expression.linear_expression(name)
 
 
-def _face_operands(pos):
+def _face_operands(pos, make=None):
     """Symbolic operands of a face normal to axis ``pos`` (0=z,1=y,2=x) in the
     plug-in argument order: (k-, k+), then (T-, T+) pairs at the face centre
     and displaced by -1/+1 along the first, the second, and both tangential
@@ -69,24 +69,74 @@ def _face_operands(pos):
         chars = [str(a), str(b)]
         chars.insert(pos, side)
         return prefix + "".join(chars)
-    k = [_operand(name("kmat", s, 5, 5)) for s in "mp"]
-    T = [_operand(name("T", s, a, b))
+    make = _operand if make is None else make
+    k = [make(name("kmat", s, 5, 5)) for s in "mp"]
+    T = [make(name("T", s, a, b))
          for (a, b) in ((5, 5), (4, 5), (6, 5), (5, 4), (5, 6), (4, 6), (6, 4)) for s in "mp"]
     return k, T
+
+
+def _plugin_engine(mod):
+    """The symbolic engine a boundary plug-in was written against: the module its ``group`` comes from (the
+    reference's plug-ins do ``from heatsim2.expression import group``, boundary_conducting.py:5).  None = ours."""
+    import sys
+    grp = getattr(mod, "group", None)
+    eng = sys.modules.get(getattr(grp, "__module__", None)) if grp is not None else None
+    if eng is None or eng is expression or not hasattr(eng, "linear_expression"):
+        return None
+    return eng
+
+
+def from_foreign_expression(expr):
+    """Convert an expression object of the REFERENCE's engine (heatsim2/expression.py: an RPN list ``le_cmdlist`` of
+    (operator, value) with OP_ADD/MUL/PARAM/VAR/GROUP/DIV, :15-27) into this package's expression tree, by running the
+    RPN program on our own operands.  Lets unmodified reference plug-ins (and user plug-ins written against
+    ``heatsim2.expression``) be handed to :func:`setup`."""
+    if isinstance(expr, numbers.Number):
+        return expr
+    if isinstance(expr, expression.linear_expression):
+        return expr
+    stack = []
+    for op, val in expr.le_cmdlist:
+        if op == expr.OP_PARAM:
+            stack.append(val)
+        elif op == expr.OP_VAR:
+            name, coef, i0, i1 = val
+            v = expression.linear_expression(name)
+            if i0 is not None or i1 is not None:
+                v = v[i0, i1]
+            stack.append(v * coef)
+        elif op == expr.OP_GROUP:
+            top = stack.pop()
+            stack.append(expression.group(top if isinstance(top, expression.linear_expression)
+                                          else expression.linear_expression(top)))
+        elif op in (expr.OP_ADD, expr.OP_MUL, expr.OP_DIV):
+            b = stack.pop()
+            a = stack.pop()
+            stack.append(a + b if op == expr.OP_ADD else (a * b if op == expr.OP_MUL else a / b))
+        else:
+            raise ValueError("unknown operator %r in a foreign expression" % (op,))
+    if len(stack) != 1:
+        raise ValueError("malformed foreign expression")
+    res = stack[0]
+    return res if isinstance(res, expression.linear_expression) else expression.linear_expression(res)
 
 
 def evaluate_boundaries(boundaries, dz, dy, dx):
     """Flux expression through a z-, y- and x-face for every boundary class
     (reference :220-250): the plug-in's ``qz/qy/qx`` are called once with
     symbolic operands centred on the face; extra elements of the boundary
-    tuple are passed through as trailing arguments."""
+    tuple are passed through as trailing arguments.  A plug-in written against
+    another engine with the reference's data model (``heatsim2.expression``) gets
+    operands of ITS engine and its result is converted (:func:`from_foreign_expression`)."""
     out = []
     for boundary in boundaries:
         mod, extra = boundary[0], list(boundary[1:])
+        eng = _plugin_engine(mod)
         fluxes = []
         for pos, fn in enumerate((mod.qz, mod.qy, mod.qx)):
-            k, T = _face_operands(pos)
-            fluxes.append(fn(k[0], k[1], dz, dy, dx, *(T + extra)))
+            k, T = _face_operands(pos, None if eng is None else eng.linear_expression)
+            fluxes.append(from_foreign_expression(fn(k[0], k[1], dz, dy, dx, *(T + extra))))
         out.append(tuple(fluxes))
     return out
 

@@ -606,22 +606,62 @@ class AdiPlan(object):
         self._check_field(arr)
         self.ensure_device()
         with torch.cuda.device(self._dev):
-            stage_in = self._pinned("pin_in")
-            stage_in.copy_(torch.from_numpy(arr))
             d_T = self._buf("T")
-            d_T.copy_(stage_in, non_blocking=True)
+            self._upload(torch.from_numpy(arr), d_T)
             self.step_device(d_T, d_T, t, dt, volumetric_elements, volumetric)
-            stage_out = self._pinned("pin_out")
-            stage_out.copy_(d_T, non_blocking=True)
-            torch.cuda.current_stream(self._dev).synchronize()
-            return stage_out.numpy().copy()
+            result = torch.empty(self.shape, dtype=torch.float64)       # the new array the caller gets, like the reference
+            self._download(d_T, result)
+            return result.numpy()
 
-    def _pinned(self, name):
-        b = self._bufs.get(name)
+    # numpy in / numpy out (the reference's contract): the user's arrays are pageable, so they travel through two
+    # pinned staging chunks; the host memcpy of chunk i+1 (torch's multi-threaded copy) overlaps the DMA of chunk i
+    STAGE_BYTES = 64 << 20
+
+    def _staging(self):
+        b = self._bufs.get("stage")
         if b is None:
-            b = torch.empty(self.shape, dtype=torch.float64).pin_memory()
-            self._bufs[name] = b
-        return b
+            b = [torch.empty(self.STAGE_BYTES // 8, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._bufs["stage"] = b
+            self._bufs["stage_ev"] = [torch.cuda.Event() for _ in range(2)]
+        return b, self._bufs["stage_ev"]
+
+    def _upload(self, host, dev):
+        """pageable host tensor -> device tensor, on the current stream"""
+        stage, ev = self._staging()
+        src, dst = host.reshape(-1), dev.reshape(-1)
+        n, step = src.numel(), stage[0].numel()
+        stream = torch.cuda.current_stream(self._dev)
+        for c, o in enumerate(range(0, n, step)):
+            m = min(step, n - o)
+            b = c & 1
+            ev[b].synchronize()                       # the DMA that last read this staging buffer is done
+            stage[b][:m].copy_(src[o:o + m])
+            dst[o:o + m].copy_(stage[b][:m], non_blocking=True)
+            ev[b].record(stream)
+
+    def _download(self, dev, host):
+        """device tensor -> pageable host tensor; returns when the data is there"""
+        stage, ev = self._staging()
+        src, dst = dev.reshape(-1), host.reshape(-1)
+        n, step = src.numel(), stage[0].numel()
+        stream = torch.cuda.current_stream(self._dev)
+        ev[0].synchronize()
+        ev[1].synchronize()
+        pending = None
+        for c, o in enumerate(range(0, n, step)):
+            m = min(step, n - o)
+            b = c & 1
+            stage[b][:m].copy_(src[o:o + m], non_blocking=True)
+            ev[b].record(stream)
+            if pending is not None:
+                pb, po, pm = pending
+                ev[pb].synchronize()
+                dst[po:po + pm].copy_(stage[pb][:pm])
+            pending = (b, o, m)
+        if pending is not None:
+            pb, po, pm = pending
+            ev[pb].synchronize()
+            dst[po:po + pm].copy_(stage[pb][:pm])
 
     # ------------------------------------------- host inspection (small grids)
     def reference_matrices(self, stepnum):
@@ -763,7 +803,20 @@ class CellwiseBuilder(object):
             self.coefs.append((M,) + tuple(g) + (D,))
         self.class_id[k, j, i] = c
 
+    def add_stage(self, stepnum, pos, eqdict):
+        """one stage's dictionary of one cell (pyadi_step.add_equation); the cell is classified as soon as all three
+        stages are there"""
+        pending = self.__dict__.setdefault("_pending", {})
+        entry = pending.setdefault(pos, [None, None, None])
+        entry[stepnum] = eqdict
+        if all(d is not None for d in entry):
+            key = tuple(tuple(sorted(d.items())) for d in entry)
+            self.add(pos[0], pos[1], pos[2], key, entry)
+            del pending[pos]
+
     def finish(self, dt, volume_array):
+        if getattr(self, "_pending", None):
+            raise ValueError("%d cells have equations for some stages only" % len(self._pending))
         if (self.class_id < 0).any():
             raise ValueError("some cells have no equation")
         return AdiPlan(self.shape, self.class_id, np.array(self.coefs), dt, volume_array)
