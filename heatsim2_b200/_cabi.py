@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HS2_B200_LIB") or os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -24,7 +24,8 @@ class AxisTables(ctypes.Structure):
         ("d_tab", c_void_p), ("d_GE", c_void_p), ("d_tab_il", c_void_p),
         ("h_utab", c_void_p), ("d_ucode", c_void_p),
         ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
-        ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("xw_band", ctypes.c_int32),
+        ("d_xw_tab", c_void_p), ("d_xw_code", c_void_p),
     ]
 
 

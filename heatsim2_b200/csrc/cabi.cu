@@ -13,6 +13,10 @@ void hs2_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static bool has_source(const hs2_source *src) {
+  return src && ((src->h_value && src->d_vol_elements) || src->d_dense);
+}
+
 extern "C" {
 
 int hs2_abi_version(void) { return HS2_ABI_VERSION; }
@@ -83,6 +87,7 @@ int hs2_plan_launches_per_step(const hs2_plan *plan) {
 
 int hs2_plan_x_kernel(const hs2_plan *plan) {
   if (!plan) return -1;
+  if (hs2_tile_xw_supported(plan)) return HS2_XK_WARP;
   if (hs2_tile_xt_supported(plan)) return HS2_XK_TMA;
   if (!hs2_tile_xf_supported(plan)) return HS2_XK_WHOLE_LINE;
   return HS2_XK_FOLD;
@@ -95,7 +100,7 @@ int hs2_plan_last_kernel(const hs2_plan *plan, int axis) {
 
 const char *hs2_kernel_name(int code) {
   static const char *const names[] = {"none", "whole-line", "tile", "tile-tma", "tile-tma-512", "tile-cpasync",
-                                      "tile-cpasync-512", "x-fold", "z-slab", "x-tma"};
+                                      "tile-cpasync-512", "x-fold", "z-slab", "x-tma", "x-warp"};
   return (code >= 0 && code < (int)(sizeof(names) / sizeof(names[0]))) ? names[code] : "?";
 }
 
@@ -103,6 +108,11 @@ int hs2_sweep_x(hs2_plan *plan, const double *d_T_in, double *d_work, const hs2_
                 const double *d_halo_hi, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x: d_work must not alias d_T_in");
+  if (!has_source(src) && hs2_tile_xw_supported(plan)) {
+    bool done = false;
+    int rc = hs2_tile_sweep_xw(plan, d_T_in, d_work, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream, &done);
+    if (rc || done) return rc;
+  }
   if (hs2_tile_xt_supported(plan)) {
     bool done = false;
     int rc = hs2_tile_sweep_xt(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, 0, (cudaStream_t)stream, &done);
@@ -118,6 +128,11 @@ int hs2_sweep_x_part(hs2_plan *plan, const double *d_T_in, double *d_work, const
   HS2_REQUIRE(plan && d_T_in && d_work, "hs2_sweep_x_part: NULL argument");
   HS2_REQUIRE(d_T_in != d_work, "hs2_sweep_x_part: d_work must not alias d_T_in");
   HS2_REQUIRE(part == HS2_X_INTERIOR || part == HS2_X_BOUNDARY, "hs2_sweep_x_part: part must be HS2_X_INTERIOR or HS2_X_BOUNDARY");
+  if (!has_source(src) && hs2_tile_xw_supported(plan) && plan->d.nz >= 3) {
+    bool done = false;
+    int rc = hs2_tile_sweep_xw(plan, d_T_in, d_work, d_halo_lo, d_halo_hi, part, (cudaStream_t)stream, &done);
+    if (rc || done) return rc;
+  }
   if (hs2_tile_xt_supported(plan) && plan->d.nz >= 3) {
     bool done = false;
     int rc = hs2_tile_sweep_xt(plan, d_T_in, d_work, src, d_halo_lo, d_halo_hi, part, (cudaStream_t)stream, &done);

@@ -76,6 +76,10 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
 bool hs2_tile_xt_supported(const hs2_plan *p);
 int hs2_tile_sweep_xt(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,
                       const double *halo_hi, int part, cudaStream_t st, bool *done);
+// kernels_xw.cu - x sweep, one warp per line (nx = 512, source-free steps); *done = false: fall through
+bool hs2_tile_xw_supported(const hs2_plan *p);
+int hs2_tile_sweep_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, const double *halo_hi, int part,
+                      cudaStream_t st, bool *done);
 // kernels_xf.cu - x sweep with the explicit x-term folded into the solve
 bool hs2_tile_xf_supported(const hs2_plan *p);
 int hs2_tile_sweep_xf(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,

@@ -64,10 +64,101 @@ def thomas_factors(lo, dg, hi):
     return out
 
 
+XW_HDR = 128          # doubles per unique line in front of its interface rows (hs2_axis_tables.d_xw_tab)
+
+
+def x_warp_applies(nx):
+    """The warp-per-line x sweep (csrc/kernels_xw.cu) takes lines of exactly 32 chunks of 16 cells;
+    HS2_X_KERNEL=tma keeps the patch kernel, =fold the LSU-fed one."""
+    return os.environ.get("HS2_X_KERNEL", "warp") == "warp" and nx == 512
+
+
+def ghost_uniform_tables(lo, dg, hi, M, tol=1e-16):
+    """Tables of the warp-per-line x kernel for the unique lines that have constant coefficients and closed ends:
+    rows 1..L-2 identical (a, b, c), row 0 = (0, b + a, c), row L-1 = (a, b + c, 0) (to 4 ulp) - a homogeneous line
+    between two insulated / closed faces.  Such a line equals the infinite constant-coefficient line with MIRRORED
+    ghost neighbours (x_{-1} = x_0, x_L = x_{L-1}), so that every one of its chunks, the first and the last included,
+    can be eliminated with ONE chunk table; the mirror only enters the interface system (alpha_0 = F_0, the first
+    value of the line; F_P = E_{P-1}) and the back substitution of the first chunk, x = a - F_0 b with
+    b_k = s_k - cp_k b_{k+1} and F_0 = a_0 / (1 + b_0).
+
+    lo, dg, hi: [n_unique, L].  Returns (code uint8 [n_unique], xw [n_unique, XW_HDR + (2 band + 1) * 64], band):
+    xw[u, 0:80] planes inv, f, c, s, cp of the common chunk, xw[u, 80:96] b, xw[u, 96] 1 / (1 + b_0), then
+    [2 band + 1][P][2] the rows of the inverse interface operator that give E_p, relative to the diagonal
+    (entry d of chunk p multiplies (y_first, y_last) of chunk p + d - band; 0 outside the line); band: half-width
+    beyond which all entries are below ``tol`` of their row maximum."""
+    nu, L = dg.shape
+    P = L // M
+    code = np.zeros(nu, dtype=np.uint8)
+    if L != P * M or L < 3 * M:
+        return code, np.zeros((nu, XW_HDR + 64)), 0
+    a, b, c = lo[:, 1], dg[:, 1], hi[:, 1]
+    eps = 4 * np.finfo(float).eps
+    ok = (lo[:, 1:] == a[:, None]).all(axis=1) & (hi[:, :-1] == c[:, None]).all(axis=1) & \
+         (dg[:, 1:-1] == b[:, None]).all(axis=1) & (lo[:, 0] == 0.0) & (hi[:, -1] == 0.0) & \
+         (np.abs(dg[:, 0] - (b + a)) <= eps * np.abs(b)) & (np.abs(dg[:, -1] - (b + c)) <= eps * np.abs(b))
+    code[:] = ok
+    sel = np.nonzero(ok)[0]
+    if len(sel) == 0:
+        return code, np.zeros((nu, XW_HDR + 64)), 0
+    ns = len(sel)
+    # the common chunk: rows (a, b, c) throughout, coupled to its left neighbour through row 0
+    tab, _ = chunk_factors(np.repeat(a[sel, None], M, 1), np.repeat(b[sel, None], M, 1), np.repeat(c[sel, None], M, 1), M)
+    inv, f, cc, s, cp = (tab[:, pl, :M] for pl in range(T_PLANES))
+    f = f.copy()
+    f[:, 0] = 0.0
+    v0 = np.zeros(ns)
+    c_cur = np.ones(ns)
+    for r in range(M):
+        v0 += c_cur * s[:, r]
+        c_cur = -cp[:, r] * c_cur
+    cm, sl, cpl = c_cur, s[:, M - 1], cp[:, M - 1]
+    R = np.zeros((ns, 2 * P, 2 * P))
+    idx = np.arange(P)
+    R[:, idx, idx] = 1.0
+    R[:, P + idx, P + idx] = 1.0
+    for p in range(P):
+        if p > 0:
+            R[:, p, P + p - 1] = v0
+            R[:, P + p, P + p - 1] = sl
+        else:                       # mirrored ghost: alpha_0 = F_0
+            R[:, 0, 0] += v0
+            R[:, P, 0] += sl
+        if p < P - 1:
+            R[:, p, p + 1] = -cm
+            R[:, P + p, p + 1] = cpl
+        else:                       # mirrored ghost: F_P = E_{P-1}
+            R[:, p, P + p] += -cm
+            R[:, P + p, P + p] += cpl
+    Rinv = np.linalg.inv(R)
+    GE = np.zeros((ns, P, 2 * P))
+    GE[:, :, 0::2] = Rinv[:, P:, :P]
+    GE[:, :, 1::2] = Rinv[:, P:, P:]
+    band = interface_band(GE, tol)
+    bt = np.zeros((ns, M))
+    for k in range(M - 2, -1, -1):
+        bt[:, k] = s[:, k] - cp[:, k] * bt[:, k + 1]
+    w = 2 * band + 1
+    xw = np.zeros((nu, XW_HDR + w * P * 2))
+    hdr = np.zeros((ns, XW_HDR))
+    for pl, t in enumerate((inv, f, cc, s, cp, bt)):
+        hdr[:, pl * M:(pl + 1) * M] = t
+    hdr[:, 6 * M] = 1.0 / (1.0 + bt[:, 0])
+    rel = np.zeros((ns, w, P, 2))
+    for d in range(w):
+        q = idx + d - band
+        inside = (q >= 0) & (q < P)
+        rel[:, d, idx[inside], 0] = GE[:, idx[inside], 2 * q[inside]]
+        rel[:, d, idx[inside], 1] = GE[:, idx[inside], 2 * q[inside] + 1]
+    xw[sel, :XW_HDR] = hdr
+    xw[sel, XW_HDR:] = rel.reshape(ns, -1)
+    return code, xw, band
+
+
 def x_tma_applies(nx):
     """The TMA-fed x sweep (csrc/kernels_xt.cu) takes lines of 16..512 cells, a multiple
     of 16 (one 128-byte segment per thread); HS2_X_KERNEL=fold keeps the LSU-fed kernel."""
-    return os.environ.get("HS2_X_KERNEL", "tma") != "fold" and nx % 16 == 0 and 16 <= nx <= 512
+    return os.environ.get("HS2_X_KERNEL", "warp") != "fold" and nx % 16 == 0 and 16 <= nx <= 512
 
 
 def choose_chunk(L, axis=None):
@@ -79,8 +170,8 @@ def choose_chunk(L, axis=None):
     HS2_CHUNK_X for the x axis) with at least 4 chunks is taken, else the
     largest valid M.  (0, 0): too long for the register-tile kernels
     (whole-line fallback)."""
-    if axis == 0 and x_tma_applies(L):
-        return 16, L // 16                 # kernels_xt.cu: one 128-byte segment per thread
+    if axis == 0 and (x_tma_applies(L) or x_warp_applies(L)):
+        return 16, L // 16                 # kernels_xt.cu / kernels_xw.cu: one 128-byte segment per thread
     valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
     if not valid:
         return 0, 0
@@ -264,8 +355,10 @@ class AdiPlan(object):
         # HS2_NO_UTAB=1: every chunk reads its factor tables (A/B of the constant-bank fast path)
         if os.environ.get("HS2_NO_UTAB", "0") == "1":
             self.flags |= 4
-        if os.environ.get("HS2_X_KERNEL", "tma") == "fold":
+        if os.environ.get("HS2_X_KERNEL", "warp") == "fold":
             self.flags |= 16
+        if os.environ.get("HS2_X_KERNEL", "warp") == "tma":
+            self.flags |= 32
         # axes whose kernels take the constant-bank table (measured on B200, profiles/NOTES_r02.md)
         self.utab_axes = os.environ.get("HS2_UTAB_AXES", "xz")     # x: the TMA-fed kernel; z: strided_sweep_tma<FINAL>
         self._bufs = {}
@@ -338,7 +431,7 @@ class AdiPlan(object):
     def x_kernel(self):
         """'whole-line' or 'fold': the kernel a whole-grid hs2_sweep_x of this plan runs"""
         self.ensure_device()
-        return ("whole-line", "fold", "tma")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
+        return ("whole-line", "fold", "tma", "warp")[int(_cabi.lib().hs2_plan_x_kernel(self._handle))]
 
     def last_kernels(self):
         """names of the kernel variants the last x, y and z sweeps of this plan launched
@@ -394,6 +487,11 @@ class AdiPlan(object):
                     self._d_ucode[a] = torch.from_numpy(ucode).to(dev)
                     ax.h_utab = self._utab[a].ctypes.data
                     ax.d_ucode = self._d_ucode[a].data_ptr()
+                if a == 0 and x_warp_applies(self.shape[2]) and self.chunk[0] == (16, 32) and self.n_classes <= 64:
+                    code, xw, xw_band = ghost_uniform_tables(*self.line_rows[0], 16)
+                    self.d_xw_code = torch.from_numpy(code).to(dev)
+                    self.d_xw_tab = torch.from_numpy(np.ascontiguousarray(xw)).to(dev)
+                    ax.d_xw_code, ax.d_xw_tab, ax.xw_band = self.d_xw_code.data_ptr(), self.d_xw_tab.data_ptr(), xw_band
                 if a == 0:
                     M, P = self.chunk[0]
                     self.d_tab_il = torch.from_numpy(interleave_chunks(self.chunk_tabs[0][0], self.shape[2], M, P)).to(dev)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS2_ABI_VERSION 3
+#define HS2_ABI_VERSION 4
 
 #define HS2_OK 0
 #define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
@@ -69,6 +69,16 @@ extern "C" {
  *                                          bank) and read it without loads
  *   d_ucode [n_unique][n_chunks] (u8)      1 where chunk p of unique line u
  *                                          equals h_utab bit for bit, else 0
+ *   d_xw_tab [n_unique][128 + (2*xw_band+1)*64]  (x axis only, may be NULL; the warp-per-line
+ *                                          kernel, lines of 32 chunks of 16) per unique line
+ *                                          with constant coefficients and closed ends: [0..79] the
+ *                                          common chunk table (planes as d_tab, 16 rows each),
+ *                                          [80..95] b (correction of the first chunk), [96] 1/(1+b_0),
+ *                                          then [2*xw_band+1][32 chunks][2] rows of the inverse
+ *                                          interface operator with mirrored ghost neighbours,
+ *                                          diagonal-relative (entry d of chunk p multiplies chunk
+ *                                          p + d - xw_band; 0 outside the line)
+ *   d_xw_code [n_unique] (u8)              1 where d_xw_tab describes the line, else 0
  * chunk == 0 means the tables are absent and the whole-line path is used.   */
 #define HS2_T_INV 0
 #define HS2_T_F 1
@@ -90,7 +100,9 @@ typedef struct hs2_axis_tables {
   int32_t n_chunks;
   int32_t pitch;             /* doubles per table plane (even, >= L)           */
   int32_t band;              /* half-width (in chunks) of d_GE rows worth applying */
-  int32_t reserved;
+  int32_t xw_band;           /* the same for the rows in d_xw_tab                  */
+  const double *d_xw_tab;    /* device, or NULL                                  */
+  const uint8_t *d_xw_code;  /* device, or NULL                                  */
 } hs2_axis_tables;
 
 /* Axis numbering used by every per-axis array: 0 = x (contiguous), 1 = y,
@@ -117,7 +129,8 @@ typedef struct hs2_plan_desc {
 
 #define HS2_FLAG_FORCE_FALLBACK 1 /* use the whole-line global-memory kernels */
 #define HS2_FLAG_NO_UTAB 4        /* ignore h_utab / d_ucode (every chunk reads its factor tables) */
-#define HS2_FLAG_X_FOLD 16        /* x sweep: keep the folded LSU-fed kernel even where the TMA-fed one applies */
+#define HS2_FLAG_X_FOLD 16        /* x sweep: keep the folded LSU-fed kernel even where the TMA-fed ones apply */
+#define HS2_FLAG_X_PATCH 32       /* x sweep: keep the TMA-fed patch kernel where the warp-per-line kernel applies */
 
 typedef struct hs2_plan hs2_plan;
 
@@ -148,11 +161,13 @@ int hs2_plan_destroy(hs2_plan *plan);
 int hs2_plan_launches_per_step(const hs2_plan *plan);
 
 /* which kernel a whole-grid hs2_sweep_x of this plan runs: whole-line
- * global-memory fallback (rhs + Thomas), the folded tile kernel or the
- * TMA-fed patch kernel                                                       */
+ * global-memory fallback (rhs + Thomas), the folded tile kernel, the
+ * TMA-fed patch kernel or the TMA-fed warp-per-line kernel (source-free steps;
+ * steps with a volumetric source run the patch kernel)                       */
 #define HS2_XK_WHOLE_LINE 0
 #define HS2_XK_FOLD 1
 #define HS2_XK_TMA 2
+#define HS2_XK_WARP 3
 int hs2_plan_x_kernel(const hs2_plan *plan);
 
 /* Which kernel variant the LAST sweep along `axis` (0 = x, 1 = y, 2 = z) of
@@ -169,6 +184,7 @@ int hs2_plan_x_kernel(const hs2_plan *plan);
 #define HS2_K_X_FOLD 7         /* sweep_xf_kernel                                        */
 #define HS2_K_Z_SLAB 8         /* z_forward / z_backward of a slab plan                  */
 #define HS2_K_X_TMA 9          /* sweep_xt_kernel: patches staged by TMA, chunk-layout RHS */
+#define HS2_K_X_WARP 10        /* sweep_xw_kernel: one warp per line, interfaces by shuffle */
 int hs2_plan_last_kernel(const hs2_plan *plan, int axis);
 const char *hs2_kernel_name(int code);
 

@@ -49,15 +49,18 @@ def _steps_vs_oracle(hs, prob, nsteps, restart=True):
 
 # (problem, kwargs, long axis 0=x 1=y 2=z, expected (chunk rows, chunks) on it, expected kernel on it)
 LONG_LINES = [
-    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (16, 32), "x-tma"),
+    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (16, 32), "x-warp"),
+    ("uniform_slab", dict(shape=(21, 47, 512)), 0, (16, 32), "x-warp"),     # odd plane count, ragged row patches, several patches per group
+    ("steelonfoam", dict(nz=12, ny=20, nx=512, nsteps=3), 0, (16, 32), "x-warp"),   # delamination gap: lines with a class change inside
     ("uniform_slab", dict(shape=(8, 512, 16)), 1, (32, 16), "tile-tma"),
     ("uniform_slab", dict(shape=(512, 8, 16)), 2, (32, 16), "tile-cpasync"),
     ("uniform_slab", dict(shape=(8, 16, 1024)), 0, (32, 32), "x-fold"),
     ("uniform_slab", dict(shape=(8, 1024, 16)), 1, (32, 32), "tile-tma-512"),
     ("uniform_slab", dict(shape=(1024, 8, 16)), 2, (32, 32), "tile-cpasync-512"),
     # several unique lines along the long axis (material change, thin layer, delamination)
-    ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (16, 32), "x-tma"),
-    ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-tma"),      # odd plane count, ragged row patches
+    ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (16, 32), "x-warp"),
+    ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-warp"),      # odd plane count, ragged row patches
+    ("composite", dict(nz=19, ny=10, nx=512), 0, (16, 32), "x-warp"),
     ("composite", dict(nz=19, ny=10, nx=256), 0, (16, 16), "x-tma"),
     ("steelonwater", dict(nz=8, ny=512, nx=16), 1, (32, 16), "tile-tma"),
     ("composite", dict(nz=512, ny=8, nx=16), 2, (32, 16), "tile-cpasync"),
@@ -69,11 +72,43 @@ LONG_LINES = [
 ]
 
 
-# the LSU-fed folded x kernel (kernels_xf.cu) stays the path of lines the TMA kernel does not take; forced here at 512
+# the LSU-fed folded x kernel (kernels_xf.cu) stays the path of lines the TMA kernels do not take; forced here at 512
 FOLD_LINES = [
     ("uniform_slab", dict(shape=(8, 16, 512)), 0, (32, 16), "x-fold"),
     ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (32, 16), "x-fold"),
 ]
+
+# the TMA-fed patch kernel (kernels_xt.cu) runs the steps with a volumetric source and the lines of 16..496 cells;
+# forced here at 512 (HS2_X_KERNEL=tma)
+PATCH_LINES = [
+    ("uniform_slab", dict(shape=(8, 16, 512)), 0, (16, 32), "x-tma"),
+    ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-tma"),
+]
+
+
+@pytest.mark.parametrize("name,kwargs,axis,chunk,kernel", PATCH_LINES)
+def test_patch_x_kernel_vs_oracle(hs, monkeypatch, name, kwargs, axis, chunk, kernel):
+    monkeypatch.setenv("HS2_X_KERNEL", "tma")
+    test_long_lines_vs_oracle(hs, name, kwargs, axis, chunk, kernel)
+
+
+@pytest.mark.parametrize("shape", ["33", "52", "42"])
+def test_warp_x_kernel_shapes_vs_oracle(hs, shape):
+    """both patch shapes of the warp-per-line kernel (HS2_XW_SHAPE is read once per process: subprocess)"""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = %r; import numpy as np, torch, heatsim2_b200 as hs, adi_oracle, problems, util\n"
+            "for name, kw in (('uniform_slab', dict(shape=(21, 47, 512))), ('steelonwater', dict(nz=9, ny=14, nx=512)),\n"
+            "                 ('steelonfoam', dict(nz=12, ny=20, nx=512, nsteps=3))):\n"
+            "    prob = problems.ALL[name](hs, **kw)\n"
+            "    got = util.run_b200(hs, prob, nsteps=3)\n"
+            "    err = util.relerr(got, adi_oracle.run(prob, nsteps=3))\n"
+            "    assert err <= 3e-12, (name, err)\n"
+            "print('ok')\n") % ([p for p in sys.path if p],)
+    env = dict(os.environ, HS2_XW_SHAPE=shape)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("name,kwargs,axis,chunk,kernel", FOLD_LINES)
@@ -137,7 +172,7 @@ def test_survey_sizes_vs_reference_digests(hs, case):
     if cols:
         got = torch.stack(hist).cpu().numpy()
         assert util.relerr(got, z["surface_hist"]) <= TOL_RUN
-    assert all(k.startswith("tile") or k == "x-tma" for k in P.plan.last_kernels()), P.plan.last_kernels()
+    assert all(k.startswith("tile") or k in ("x-tma", "x-warp") for k in P.plan.last_kernels()), P.plan.last_kernels()
 
 
 def test_c2_64_1000_steps_vs_oracle(hs):
