@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HS2_B200_LIB") or os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -44,6 +44,30 @@ class Source(ctypes.Structure):
     _fields_ = [("d_vol_elements", c_void_p), ("h_value", c_double_p), ("d_dense", c_void_p)]
 
 
+class BuildDesc(ctypes.Structure):
+    _fields_ = [
+        ("nz", ctypes.c_int64), ("ny", ctypes.c_int64), ("nx", ctypes.c_int64),
+        ("n_classes", ctypes.c_int32), ("class_id_bytes", ctypes.c_int32),
+        ("d_class_id", c_void_p), ("h_class_coef", c_double_p),
+        ("device", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("chunk", ctypes.c_int32 * 3), ("utab_axes", ctypes.c_int32),
+        ("d_class_id_global", c_void_p), ("nz_global", ctypes.c_int64), ("k0", ctypes.c_int64),
+    ]
+
+
+class AxisInfo(ctypes.Structure):
+    _fields_ = [
+        ("line_length", ctypes.c_int64), ("n_lines", ctypes.c_int64),
+        ("n_unique", ctypes.c_int32), ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
+        ("pitch", ctypes.c_int32), ("band", ctypes.c_int32), ("xw_band", ctypes.c_int32),
+    ]
+
+
+# hs2_plan_copy_table selectors (HS2_TAB_*)
+(TAB_LINE_ID, TAB_ROWS_LO, TAB_ROWS_DG, TAB_ROWS_HI, TAB_LU, TAB_CHUNK, TAB_GE, TAB_CHUNK_IL, TAB_UTAB, TAB_UCODE, TAB_XW,
+ TAB_XW_CODE) = range(12)
+
+
 class Hs2Error(RuntimeError):
     pass
 
@@ -56,6 +80,11 @@ PROTOTYPES = {
     "hs2_last_error": (ctypes.c_char_p, []),
     "hs2_sizeof": (ctypes.c_int, [ctypes.c_int]),
     "hs2_plan_create": (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.POINTER(c_void_p)]),
+    "hs2_plan_build": (ctypes.c_int, [ctypes.POINTER(BuildDesc), ctypes.POINTER(c_void_p)]),
+    "hs2_plan_axis_info": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(AxisInfo)]),
+    "hs2_plan_copy_table": (ctypes.c_int64, [c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_int64]),
+    "hs2_tables_chunk": (ctypes.c_int, [c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        c_double_p, c_double_p]),
     "hs2_plan_destroy": (ctypes.c_int, [c_void_p]),
     "hs2_plan_launches_per_step": (ctypes.c_int, [c_void_p]),
     "hs2_plan_x_kernel": (ctypes.c_int, [c_void_p]),
@@ -102,7 +131,7 @@ def lib():
         if L.hs2_abi_version() != ABI_VERSION:
             raise ImportError("heatsim2_b200: ABI version mismatch (%d != %d); rebuild the library"
                               % (L.hs2_abi_version(), ABI_VERSION))
-        for which, struct in enumerate((AxisTables, PlanDesc, Source)):
+        for which, struct in enumerate((AxisTables, PlanDesc, Source, BuildDesc, AxisInfo)):
             if L.hs2_sizeof(which) != ctypes.sizeof(struct):
                 raise ImportError("heatsim2_b200: ctypes mirror of %s is %d bytes, the library's struct %d"
                                   % (struct.__name__, ctypes.sizeof(struct), L.hs2_sizeof(which)))

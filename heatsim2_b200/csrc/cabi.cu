@@ -28,6 +28,8 @@ int hs2_sizeof(int which) {
     case 0: return (int)sizeof(hs2_axis_tables);
     case 1: return (int)sizeof(hs2_plan_desc);
     case 2: return (int)sizeof(hs2_source);
+    case 3: return (int)sizeof(hs2_build_desc);
+    case 4: return (int)sizeof(hs2_axis_info);
   }
   return -1;
 }
@@ -58,6 +60,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
     return HS2_E_NOMEM;
   }
   p->d = *desc;
+  p->owned = nullptr;
   p->n = desc->nz * desc->ny * desc->nx;
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -76,6 +79,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
 }
 
 int hs2_plan_destroy(hs2_plan *plan) {
+  if (plan && plan->owned) hs2_owned_free(plan->owned);
   delete plan;
   return HS2_OK;
 }

@@ -12,8 +12,12 @@ struct UTab {
   double v[HS2_T_PLANES][32];   // [plane][row in chunk], rows >= chunk unused
 };
 
+struct hs2_owned;                     // plan_build.cu: device buffers and host tables of a built plan
+void hs2_owned_free(hs2_owned *o);
+
 struct hs2_plan {
   hs2_plan_desc d;
+  hs2_owned *owned;    // non-NULL for plans made by hs2_plan_build
   int64_t n;           // nz*ny*nx
   int sm_count;
   int max_smem_optin;

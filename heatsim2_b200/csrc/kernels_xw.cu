@@ -39,10 +39,8 @@
 namespace {
 
 constexpr int XW_M = 16;       // cells per chunk
-constexpr int XW_P = 32;       // chunks per line = lanes
 // template parameters of the kernel: XW_R rows per plane per patch (odd: see above), XW_G groups per block;
 // a group is 2 * XW_R warps and 2 * xw_box_rows(XW_R) + 2 * XW_R rows of shared memory
-constexpr uint32_t XW_ROW = XW_P * 128;                            // bytes per row
 constexpr int XW_HDR = 128;    // doubles per unique line in front of its interface rows
 
 struct XwRanges {              // plane ranges [k0, k1) this launch covers (hs2_sweep_x_part)
@@ -111,8 +109,11 @@ __device__ __forceinline__ bool xw_interior_one_class(const uint32_t *idw) {
   return ok;
 }
 
-__device__ __forceinline__ double xw_shfl_up(double x, int d) { return __shfl_up_sync(0xffffffffu, x, d); }
-__device__ __forceinline__ double xw_shfl_down(double x, int d) { return __shfl_down_sync(0xffffffffu, x, d); }
+// shuffles inside the P lanes that hold one line
+template <int P>
+__device__ __forceinline__ double xw_shfl_up(double x, int d) { return __shfl_up_sync(0xffffffffu, x, d, P); }
+template <int P>
+__device__ __forceinline__ double xw_shfl_down(double x, int d) { return __shfl_down_sync(0xffffffffu, x, d, P); }
 
 __device__ __forceinline__ double2 xw_lds(uint32_t a) {
   double2 r;
@@ -140,35 +141,41 @@ __device__ __forceinline__ void xw_decode(int t, const XwRanges &rg, int tiles_y
   *j0 = XW_R * (q % tiles_y);
 }
 
-template <typename CID, int XW_R, int XW_G>
-__global__ void __maxnreg__(XW_G * 2 * XW_R <= 16 ? 128 : 96)
+// XW_R rows per plane per patch, XW_G groups per block, LPW lines per warp: 1 (nx = 512, lane = chunk) or
+// 2 (nx = 256: the two half warps hold the same row of the patch's two planes)
+template <typename CID, int XW_R, int XW_G, int LPW>
+__global__ void __maxnreg__(XW_G * 2 * XW_R / LPW <= 16 ? 128 : 96)
 sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, const double *__restrict__ coef_g, int n_classes,
                 int has_halo_lo, int has_halo_hi, const uint32_t *__restrict__ line_id, const double *__restrict__ tab, int pitch,
                 const double *__restrict__ GE, int band_g, const double *__restrict__ xw_tab, const uint8_t *__restrict__ xw_code,
-                int n_slots, int ge_w, int nz, int ny, int nx, int tiles_y, int n_tiles, XwRanges rg) {
-  constexpr int XW_LINES = 2 * XW_R;
+                int n_slots, int ge_w, int nz, int ny, int tiles_y, int n_tiles, XwRanges rg) {
+  constexpr int P = 32 / LPW;                                        // chunks per line
+  constexpr int NX = P * XW_M;
+  constexpr uint32_t ROW = P * 128;                                  // bytes per row
+  constexpr int WPG = 2 * XW_R / LPW;                                // warps per group
   constexpr int CR = xw_box_rows(XW_R);                              // rows per segment in a plane box (odd)
-  constexpr uint32_t XW_CBOX = CR * XW_ROW;                          // one plane's box
-  constexpr uint32_t XW_GROUP = 2 * XW_CBOX + XW_LINES * XW_ROW;
+  constexpr uint32_t XW_CBOX = CR * ROW;                             // one plane's box
+  constexpr uint32_t XW_GROUP = 2 * XW_CBOX + 2 * XW_R * ROW;
   extern __shared__ __align__(1024) unsigned char xsm[];
   double *s_hdr = reinterpret_cast<double *>(xsm + XW_G * XW_GROUP);               // [n_slots][XW_HDR]
-  double2 *s_ge = reinterpret_cast<double2 *>(s_hdr + n_slots * XW_HDR);            // [n_slots][ge_w][32]
-  double *cfs = reinterpret_cast<double *>(s_ge + n_slots * ge_w * 32);              // [n_classes][8]
+  double2 *s_ge = reinterpret_cast<double2 *>(s_hdr + n_slots * XW_HDR);            // [n_slots][ge_w][P]
+  double *cfs = reinterpret_cast<double *>(s_ge + n_slots * ge_w * P);               // [n_classes][8]
   uint64_t *barC = reinterpret_cast<uint64_t *>(cfs + n_classes * HS2_COEF_STRIDE);  // [XW_G]
-  uint64_t *barZ = barC + XW_G;                                                      // [XW_G * XW_LINES]
-  int *cnt = reinterpret_cast<int *>(barZ + XW_G * XW_LINES);                        // [XW_G]
+  uint64_t *barZ = barC + XW_G;                                                      // [XW_G * WPG]
+  int *cnt = reinterpret_cast<int *>(barZ + XW_G * WPG);                             // [XW_G]
   uint8_t *s_code = reinterpret_cast<uint8_t *>(cnt + XW_G);                         // [n_slots]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5;
-  const int g = wrp / XW_LINES, w = wrp % XW_LINES;
-  const int pz = w / XW_R, rw = w % XW_R;
-  const int p = lane;
+  const int g = wrp / WPG, w = wrp % WPG;
+  const int pz = LPW == 1 ? w / XW_R : lane >> 4;       // plane of this lane's line within the patch
+  const int rw = LPW == 1 ? w % XW_R : w;               // row of this lane's line within the patch
+  const int p = lane & (P - 1);                         // chunk
   const int n_groups = gridDim.x * XW_G;
 
   const uint32_t gb = smem_u32(xsm) + g * XW_GROUP;
   const uint32_t sC0 = gb, sC1 = gb + XW_CBOX;
-  const uint32_t sZ = gb + 2 * XW_CBOX + w * XW_ROW;
+  const uint32_t sZ = gb + 2 * XW_CBOX + (pz * XW_R + rw) * ROW;    // this line's private row
   const uint32_t bC = smem_u32(barC + g), bZ = smem_u32(barZ + wrp);
   const uint32_t coef_s = smem_u32(cfs);
 
@@ -177,14 +184,14 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
       mbar_init(barC + q, 1);
       cnt[q] = 0;
     }
-    for (int q = 0; q < XW_G * XW_LINES; ++q) mbar_init(barZ + q, 1);
+    for (int q = 0; q < XW_G * WPG; ++q) mbar_init(barZ + q, 1);
     fence_mbar_init();
   }
   {
-    const int64_t stride = XW_HDR + ge_w * 64;
+    const int64_t stride = XW_HDR + ge_w * P * 2;
     for (int q = tid; q < n_slots * XW_HDR; q += blockDim.x) s_hdr[q] = xw_tab[(int64_t)(q / XW_HDR) * stride + q % XW_HDR];
-    for (int q = tid; q < n_slots * ge_w * 32; q += blockDim.x) {
-      const int s = q / (ge_w * 32), e = q % (ge_w * 32);
+    for (int q = tid; q < n_slots * ge_w * P; q += blockDim.x) {
+      const int s = q / (ge_w * P), e = q % (ge_w * P);
       s_ge[q] = reinterpret_cast<const double2 *>(xw_tab + (int64_t)s * stride + XW_HDR)[e];
     }
     for (int q = tid; q < n_slots; q += blockDim.x) s_code[q] = xw_code[q];
@@ -192,7 +199,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   }
   __syncthreads();
 
-  // loads of the two shared boxes of patch t (planes k0 and k0+1, rows j0-1 .. j0+XW_R); the plane above the
+  // loads of the two shared boxes of patch t (planes k0 and k0+1, rows j0-1 .. j0+CR-2); the plane above the
   // grid is the upper slab's halo plane, or zeros at a domain face (conductance 0 there)
   auto issue_C = [&](int t) {
     int r, k0, j0;
@@ -222,7 +229,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
     const int kq = kk0 + pz, jq = jj0 + rw;
     lid_out = 0;
     if (jq < ny && kq < (rr ? rg.k1[1] : rg.k1[0])) {
-      const uint4 *q4 = reinterpret_cast<const uint4 *>(cid + (((int64_t)kq * ny + jq) * nx + p * XW_M));
+      const uint4 *q4 = reinterpret_cast<const uint4 *>(cid + (((int64_t)kq * ny + jq) * NX + p * XW_M));
       const uint4 a = __ldg(q4);
       ids[0] = a.x, ids[1] = a.y, ids[2] = a.z, ids[3] = a.w;
       if (sizeof(CID) == 2) {
@@ -237,7 +244,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   };
 
   int r = 0, k0 = 0, j0 = 0;
-  uint32_t idw[NIDW], idn[NIDW];
+  uint32_t idw[NIDW];
   uint32_t lid = 0, lidn = 0;
   if (t < n_tiles) {
     xw_decode<XW_R>(t, rg, tiles_y, &r, &k0, &j0);
@@ -248,24 +255,35 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   const int band_u = (ge_w - 1) >> 1;
 
   for (; t < n_tiles; t += n_groups) {
-    const int k = k0 + pz, j = j0 + rw;
-    const bool line_ok = j < ny && k < (r ? rg.k1[1] : rg.k1[0]);
+    const int j = j0 + rw;
+    const int k1r = r ? rg.k1[1] : rg.k1[0];
+    const bool line_ok = j < ny && k0 + pz < k1r;          // this lane's line exists and belongs to the launch
+    // LPW = 2: the lower plane's line (half warp 0) exists whenever the warp has work
+    const bool warp_ok = LPW == 1 ? line_ok : (j < ny && k0 < k1r);
     const bool more = t + n_groups < n_tiles;
     int rn = 0, k0n = 0, j0n = 0;
     if (more) xw_decode<XW_R>(t + n_groups, rg, tiles_y, &rn, &k0n, &j0n);
 
-    // the private row: plane k0-1 for the lines of the lower plane, plane k0+2 for the upper plane
+    // the private rows: plane k0-1 for a line of the lower plane, plane k0+2 for the upper plane
     // (below / above the grid: the neighbouring slab's halo plane, or zeros at a domain face)
-    if (lane == 0 && line_ok) {
-      if (stored) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous d1 has left this row
-      xw_expect_tx(bZ, XW_ROW);
-      const int zk = pz == 0 ? k0 - 1 : k0 + 2;
-      if (zk < 0 && has_halo_lo)
-        xw_tma_load(sZ, &tm.HloZ, bZ, j, 0);
-      else if (zk >= nz && has_halo_hi)
-        xw_tma_load(sZ, &tm.HhiZ, bZ, j, 0);
-      else
-        xw_tma_load(sZ, &tm.Z, bZ, j, zk);
+    if (lane == 0 && warp_ok) {
+      if (stored) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous d1 has left the rows
+      const int n_ok = LPW == 1 ? 1 : (k0 + 1 < k1r ? 2 : 1);
+      xw_expect_tx(bZ, n_ok * ROW);
+#pragma unroll
+      for (int h = 0; h < LPW; ++h) {
+        const int hz = LPW == 1 ? pz : h;
+        if (h < n_ok) {
+          const int zk = hz == 0 ? k0 - 1 : k0 + 2;
+          const uint32_t dst = gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW;
+          if (zk < 0 && has_halo_lo)
+            xw_tma_load(dst, &tm.HloZ, bZ, j, 0);
+          else if (zk >= nz && has_halo_hi)
+            xw_tma_load(dst, &tm.HhiZ, bZ, j, 0);
+          else
+            xw_tma_load(dst, &tm.Z, bZ, j, zk);
+        }
+      }
     }
     xw_wait(bC, parC);
     parC ^= 1;
@@ -273,7 +291,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
     double v[XW_M];
     double cB0 = 0.0, cBd = 0.0, cB15 = 0.0;
     bool slow = false;
-    if (line_ok) {
+    if (warp_ok) {
       slow = __any_sync(0xffffffffu, !xw_interior_one_class<CID>(idw));
       // centre values first: they are also the x neighbours
 #pragma unroll
@@ -283,90 +301,47 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         v[2 * u + 1] = c.y;
       }
       // x neighbours across the chunk ends (closed outer faces: conductance 0, any finite value)
-      double xl = xw_shfl_up(v[XW_M - 1], 1);
-      double xr_end = xw_shfl_down(v[0], 1);
+      double xl = xw_shfl_up<P>(v[XW_M - 1], 1);
+      double xr_end = xw_shfl_down<P>(v[0], 1);
       if (p == 0) xl = v[0];
-      if (p == XW_P - 1) xr_end = v[XW_M - 1];
-      if (!slow) {
-        // coefficient sets: cell 0, cells 1..14 (class of cell 8), cell 15.  y and z neighbours are read one
-        // 16-byte unit ahead of the arithmetic (the loads keep their program order: volatile asm)
-        const uint32_t q0 = coef_s + xw_cell_class<CID>(idw, 0) * (HS2_COEF_STRIDE * 8);
-        const uint32_t qd = coef_s + xw_cell_class<CID>(idw, 8) * (HS2_COEF_STRIDE * 8);
-        const uint32_t q15 = coef_s + xw_cell_class<CID>(idw, 15) * (HS2_COEF_STRIDE * 8);
-        double2 ym = xw_lds(rowC - 128 + kYm), yp = xw_lds(rowC + 128 + kYp), za = xw_lds(rowA + kC);
-        double cxm, cxp, cym, cyp, cA, cB;
-        {
-          const double2 a0 = xw_lds(q0), a1 = xw_lds(q0 + 16), a2 = xw_lds(q0 + 32);
-          cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
-          cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
-          cB = cB0 = pz == 0 ? a2.x : a2.y;
+      if (p == P - 1) xr_end = v[XW_M - 1];
+      // y and z neighbours are read one 16-byte unit ahead of the arithmetic (the loads keep their program order:
+      // volatile asm).  Coefficient sets: cell 0, cells 1..14 (class of cell 8), cell 15 - or, where a chunk has a
+      // class change inside (warp-uniform `slow`), one set per cell
+      double2 ym[2], yp[2], za[2];
+      ym[0] = xw_lds(rowC - 128 + kYm), yp[0] = xw_lds(rowC + 128 + kYp), za[0] = xw_lds(rowA + kC);
+      double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (u < 7) {
+          ym[(u + 1) & 1] = xw_lds(rowC - 128 + (((u + 1) << 4) ^ kYm));
+          yp[(u + 1) & 1] = xw_lds(rowC + 128 + (((u + 1) << 4) ^ kYp));
+          za[(u + 1) & 1] = xw_lds(rowA + (((u + 1) << 4) ^ kC));
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          double2 ymn = ym, ypn = yp, zan = za;
-          if (u < 7) {
-            ymn = xw_lds(rowC - 128 + (((u + 1) << 4) ^ kYm));
-            ypn = xw_lds(rowC + 128 + (((u + 1) << 4) ^ kYp));
-            zan = xw_lds(rowA + (((u + 1) << 4) ^ kC));
+        for (int c = 0; c < 2; ++c) {
+          const int e = 2 * u + c;
+          if (slow || e <= 1 || e == XW_M - 1) {
+            const uint32_t qq = coef_s + xw_cell_class<CID>(idw, (slow || e != 1) ? e : 8) * (HS2_COEF_STRIDE * 8);
+            const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
+            cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+            cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
+            cB = pz == 0 ? a2.x : a2.y;
+            if (e == 0) cB0 = cB;
+            if (e == 1) cBd = cB;
+            if (e == XW_M - 1) cB15 = cB;
           }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int e = 2 * u + c;
-            if (e == 1 || e == XW_M - 1) {
-              const uint32_t qq = e == 1 ? qd : q15;
-              const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
-              cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
-              cA = pz == 0 ? a2.y : a2.x;
-              cB = pz == 0 ? a2.x : a2.y;
-              if (e == 1)
-                cBd = cB;
-              else
-                cB15 = cB;
-            }
-            const double tt = v[e];
-            const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
-            double rr = cxm * (xl - tt);
-            rr = fma(cxp, xr - tt, rr);
-            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
-            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
-            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
-            rr = fma(-cB, tt, rr);             // the private row adds cB * z below
-            xl = tt;
-            v[e] = rr;
-          }
-          ym = ymn, yp = ypn, za = zan;
-        }
-      } else {
-        int last_id = -1;
-        double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const double2 ym = xw_lds(rowC - 128 + ((u << 4) ^ kYm));
-          const double2 yp = xw_lds(rowC + 128 + ((u << 4) ^ kYp));
-          const double2 za = xw_lds(rowA + ((u << 4) ^ kC));
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int e = 2 * u + c;
-            const int idc = xw_cell_class<CID>(idw, e);
-            if (idc != last_id) {
-              const uint32_t qq = coef_s + idc * (HS2_COEF_STRIDE * 8);
-              const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
-              cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
-              cA = pz == 0 ? a2.y : a2.x;
-              cB = pz == 0 ? a2.x : a2.y;
-              last_id = idc;
-            }
-            const double tt = v[e];
-            const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
-            double rr = cxm * (xl - tt);
-            rr = fma(cxp, xr - tt, rr);
-            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
-            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
-            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
-            rr = fma(-cB, tt, rr);
-            xl = tt;
-            v[e] = rr;
-          }
+          const double tt = v[e];
+          const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
+          const double2 m = ym[u & 1], q = yp[u & 1], z = za[u & 1];
+          double rr = cxm * (xl - tt);
+          rr = fma(cxp, xr - tt, rr);
+          rr = fma(cym, (c ? m.y : m.x) - tt, rr);
+          rr = fma(cyp, (c ? q.y : q.x) - tt, rr);
+          rr = fma(cA, (c ? z.y : z.x) - tt, rr);
+          rr = fma(-cB, tt, rr);             // the private row adds cB * z below
+          xl = tt;
+          v[e] = rr;
         }
       }
     }
@@ -375,63 +350,61 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
     if (lane == 0) {
       __threadfence_block();
       const int old = atomicAdd(cnt + g, 1);
-      if (old == XW_LINES - 1) {
+      if (old == WPG - 1) {
         atomicExch(cnt + g, 0);
         if (more) issue_C(t + n_groups);
       }
     }
-    if (more) fetch_ids(rn, k0n, j0n, idn, lidn);     // in flight during the solve
-
-    if (line_ok) {
+    if (warp_ok) {
       xw_wait(bZ, parZ);
       parZ ^= 1;
-      if (!slow) {
+      // (LPW = 2, upper line absent: its private row was not loaded - it still holds finite values, the line's
+      //  results are not stored)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
-          v[2 * u] = fma(u == 0 ? cB0 : cBd, zb.x, v[2 * u]);
-          v[2 * u + 1] = fma(u == 7 ? cB15 : cBd, zb.y, v[2 * u + 1]);
+      for (int u = 0; u < 8; ++u) {
+        const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
+        double b0 = u == 0 ? cB0 : cBd, b1 = u == 7 ? cB15 : cBd;
+        if (slow) {
+          const double2 s0 = xw_lds(coef_s + xw_cell_class<CID>(idw, 2 * u) * (HS2_COEF_STRIDE * 8) + 32);
+          const double2 s1 = xw_lds(coef_s + xw_cell_class<CID>(idw, 2 * u + 1) * (HS2_COEF_STRIDE * 8) + 32);
+          b0 = pz == 0 ? s0.x : s0.y;
+          b1 = pz == 0 ? s1.x : s1.y;
         }
-      } else {
-        int last_id = -1;
-        double cB = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int e = 2 * u + c;
-            const int idc = xw_cell_class<CID>(idw, e);
-            if (idc != last_id) {
-              const double2 a2 = xw_lds(coef_s + idc * (HS2_COEF_STRIDE * 8) + 32);
-              cB = pz == 0 ? a2.x : a2.y;
-              last_id = idc;
-            }
-            v[e] = fma(cB, c ? zb.y : zb.x, v[e]);
-          }
-        }
+        v[2 * u] = fma(b0, zb.x, v[2 * u]);
+        v[2 * u + 1] = fma(b1, zb.y, v[2 * u + 1]);
       }
 
+    }
+    // class ids and unique-line id of the next patch's line: in flight during the solve
+    if (more)
+      fetch_ids(rn, k0n, j0n, idw, lidn);
+    else
+      lidn = 0;
+    if (warp_ok) {
       // ------------------------------------------------ partitioned solve along x, interfaces by shuffle
-      const bool uni = lid < (uint32_t)n_slots && s_code[lid] != 0;     // warp-uniform: one line per warp
+      // an absent line (LPW = 2) borrows the other half warp's unique-line id: same code path, results dropped
+      const uint32_t lid_o = LPW == 1 ? lid : __shfl_xor_sync(0xffffffffu, lid, 16);     // (all lanes take part)
+      const uint32_t lid_e = line_ok ? lid : lid_o;
+      const bool uni_l = lid_e < (uint32_t)n_slots && s_code[lid_e] != 0;
+      const bool uni = LPW == 1 ? uni_l : __all_sync(0xffffffffu, uni_l);     // warp-uniform
       if (uni) {
         TabShared ts;
-        ts.a = smem_u32(s_hdr + lid * XW_HDR);
+        ts.a = smem_u32(s_hdr + lid_e * XW_HDR);
         ts.pitch_b = XW_M * 8u;
         double last;
         const double yf = chunk_fwd<XW_M, true>(v, ts, XW_M, &last);
-        const double2 *gr = s_ge + (int)lid * ge_w * 32 + lane;          // [d][lane]
-        const double2 gc = gr[band_u * 32];
+        const double2 *gr = s_ge + (int)lid_e * ge_w * P + p;            // [d][chunk]
+        const double2 gc = gr[band_u * P];
         double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
         for (int dl = 1; dl <= band_u; ++dl) {
-          const double2 gu = gr[(band_u - dl) * 32], gd = gr[(band_u + dl) * 32];
-          e0 = fma(gu.x, xw_shfl_up(yf, dl), e0);
-          e1 = fma(gu.y, xw_shfl_up(last, dl), e1);
-          e2 = fma(gd.x, xw_shfl_down(yf, dl), e2);
-          e3 = fma(gd.y, xw_shfl_down(last, dl), e3);
+          const double2 gu = gr[(band_u - dl) * P], gd = gr[(band_u + dl) * P];
+          e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
+          e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
+          e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
+          e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
         }
         const double E = (e0 + e1) + (e2 + e3);
-        double alpha = xw_shfl_up(E, 1);
+        double alpha = xw_shfl_up<P>(E, 1);
         if (p == 0) alpha = 0.0;
         chunk_bwd<XW_M, true>(v, ts, XW_M, alpha, E);
         if (p == 0) {
@@ -443,43 +416,47 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         }
       } else {
         TabGlobal tg;
-        tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + p * XW_M;
+        tg.b = tab + ((int64_t)lid_e * HS2_T_PLANES) * pitch + p * XW_M;
         tg.pitch = pitch;
         double last;
         const double yf = chunk_fwd<XW_M, true>(v, tg, XW_M, &last);
-        const double2 *grow = reinterpret_cast<const double2 *>(GE + ((int64_t)lid * XW_P + p) * (2 * XW_P));
+        const double2 *grow = reinterpret_cast<const double2 *>(GE + ((int64_t)lid_e * P + p) * (2 * P));
         const double2 gc = grow[p];
         double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
         for (int dl = 1; dl <= band_g; ++dl) {
           const double2 gu = p - dl >= 0 ? grow[p - dl] : make_double2(0.0, 0.0);
-          const double2 gd = p + dl < XW_P ? grow[p + dl] : make_double2(0.0, 0.0);
-          e0 = fma(gu.x, xw_shfl_up(yf, dl), e0);
-          e1 = fma(gu.y, xw_shfl_up(last, dl), e1);
-          e2 = fma(gd.x, xw_shfl_down(yf, dl), e2);
-          e3 = fma(gd.y, xw_shfl_down(last, dl), e3);
+          const double2 gd = p + dl < P ? grow[p + dl] : make_double2(0.0, 0.0);
+          e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
+          e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
+          e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
+          e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
         }
         const double E = (e0 + e1) + (e2 + e3);
-        double alpha = xw_shfl_up(E, 1);
+        double alpha = xw_shfl_up<P>(E, 1);
         if (p == 0) alpha = 0.0;
         chunk_bwd<XW_M, true>(v, tg, XW_M, alpha, E);
       }
 
       // ------------------------------------------------ d1 over the private row (same swizzle) -> bulk tensor store
+      if (line_ok) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowB + ((u << 4) ^ kB)), "d"(v[2 * u]), "d"(v[2 * u + 1]) : "memory");
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowB + ((u << 4) ^ kB)), "d"(v[2 * u]), "d"(v[2 * u + 1]) : "memory");
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        xw_tma_store(&tm.O, sZ, j, k);
+#pragma unroll
+        for (int h = 0; h < LPW; ++h) {
+          const int hz = LPW == 1 ? pz : h;
+          if (k0 + hz < k1r) xw_tma_store(&tm.O, gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW, j, k0 + hz);
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       stored = true;
     }
     r = rn, k0 = k0n, j0 = j0n;
     lid = lidn;
-#pragma unroll
-    for (int q = 0; q < NIDW; ++q) idw[q] = idn[q];
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -506,11 +483,11 @@ bool xw_encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int r
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename CID, int XW_R, int XW_G>
+template <typename CID, int XW_R, int XW_G, int LPW>
 int launch_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, const double *halo_hi, int part,
               cudaStream_t st, bool *done) {
-  constexpr int XW_LINES = 2 * XW_R;
-  constexpr uint32_t XW_GROUP = (2 * xw_box_rows(XW_R) + 2 * XW_R) * XW_ROW;
+  constexpr int P = 32 / LPW, WPG = 2 * XW_R / LPW;
+  constexpr uint32_t XW_GROUP = (2 * xw_box_rows(XW_R) + 2 * XW_R) * P * 128;
   *done = false;
   const hs2_plan_desc &d = p->d;
   const hs2_axis_tables &ax = d.axis[0];
@@ -538,23 +515,23 @@ int launch_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, co
   if (halo_lo && !xw_encode4(&tm.HloZ, halo_lo, nx, ny, 1, 1)) return HS2_OK;
   if (halo_hi && (!xw_encode4(&tm.HhiC, halo_hi, nx, ny, 1, xw_box_rows(XW_R)) || !xw_encode4(&tm.HhiZ, halo_hi, nx, ny, 1, 1))) return HS2_OK;
   const int ge_w = 2 * ax.xw_band + 1;
-  const size_t per_slot = (size_t)XW_HDR * 8 + (size_t)ge_w * 32 * 16 + 1;
+  const size_t per_slot = (size_t)XW_HDR * 8 + (size_t)ge_w * P * 16 + 1;
   const size_t fixed = (size_t)XW_G * XW_GROUP + (size_t)d.n_classes * HS2_COEF_STRIDE * 8 +
-                       (size_t)(XW_G + XW_G * XW_LINES) * 8 + XW_G * 4 + 64;
+                       (size_t)(XW_G + XW_G * WPG) * 8 + XW_G * 4 + 64;
   if (fixed + 1024 > (size_t)p->max_smem_optin) return HS2_OK;
   int n_slots = (int)(((size_t)p->max_smem_optin - 1024 - fixed) / per_slot);
   if (n_slots > ax.n_unique) n_slots = ax.n_unique;
   if (n_slots > 64) n_slots = 64;
   const size_t smem = fixed + (size_t)n_slots * per_slot;
-  auto kern = sweep_xw_kernel<CID, XW_R, XW_G>;
+  auto kern = sweep_xw_kernel<CID, XW_R, XW_G, LPW>;
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = p->sm_count;
   const int64_t need = (n_tiles + XW_G - 1) / XW_G;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, XW_G * XW_LINES * 32, smem, st>>>(tm, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes,
-                                                             halo_lo ? 1 : 0, halo_hi ? 1 : 0, ax.d_line_id, ax.d_tab, ax.pitch,
-                                                             ax.d_GE, ax.band, ax.d_xw_tab, ax.d_xw_code, n_slots, ge_w, nz, ny, nx,
-                                                             tiles_y, (int)n_tiles, rg);
+  kern<<<(unsigned)blocks, XW_G * WPG * 32, smem, st>>>(tm, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes,
+                                                        halo_lo ? 1 : 0, halo_hi ? 1 : 0, ax.d_line_id, ax.d_tab, ax.pitch, ax.d_GE,
+                                                        ax.band, ax.d_xw_tab, ax.d_xw_code, n_slots, ge_w, nz, ny, tiles_y,
+                                                        (int)n_tiles, rg);
   HS2_CUDA_CHECK(cudaGetLastError());
   p->last_kernel[0] = HS2_K_X_WARP;
   *done = true;
@@ -569,9 +546,10 @@ int launch_xw_v(hs2_plan *p, const double *T, double *W, const double *halo_lo, 
   //               42 = patches of 2 x 4 rows (7-row boxes), two groups (16 warps, 128 registers)
   // (a scheduler's quarter of the register file holds 4 warps of 128 or 5 of 96 registers)
   const int shape = getenv("HS2_XW_SHAPE") ? atoi(getenv("HS2_XW_SHAPE")) : 42;
-  if (shape == 52) return launch_xw<CID, 5, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
-  if (shape == 33) return launch_xw<CID, 3, 3>(p, T, W, halo_lo, halo_hi, part, st, done);
-  return launch_xw<CID, 4, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
+  if (p->d.nx == 256) return launch_xw<CID, 4, 4, 2>(p, T, W, halo_lo, halo_hi, part, st, done);   // 2 lines per warp
+  if (shape == 52) return launch_xw<CID, 5, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
+  if (shape == 33) return launch_xw<CID, 3, 3, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
+  return launch_xw<CID, 4, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
 }
 
 }  // namespace
@@ -581,7 +559,7 @@ bool hs2_tile_xw_supported(const hs2_plan *p) {
   const hs2_axis_tables &ax = d.axis[0];
   if (d.flags & (HS2_FLAG_FORCE_FALLBACK | HS2_FLAG_X_FOLD | HS2_FLAG_X_PATCH)) return false;
   if (ax.chunk != XW_M || !ax.d_tab || !ax.d_GE || ax.pitch <= 0 || !ax.d_xw_tab || !ax.d_xw_code || ax.xw_band < 0) return false;
-  if (d.nx != XW_M * XW_P || ax.n_chunks != XW_P || d.n_classes > 64) return false;
+  if ((d.nx != 512 && d.nx != 256) || ax.n_chunks != d.nx / XW_M || d.n_classes > 64) return false;
   if (d.ny >= ((int64_t)1 << 30) || d.nz >= ((int64_t)1 << 30)) return false;
   if ((reinterpret_cast<uintptr_t>(d.d_class_id) & 15)) return false;
   return true;

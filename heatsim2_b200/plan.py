@@ -68,9 +68,9 @@ XW_HDR = 128          # doubles per unique line in front of its interface rows (
 
 
 def x_warp_applies(nx):
-    """The warp-per-line x sweep (csrc/kernels_xw.cu) takes lines of exactly 32 chunks of 16 cells;
-    HS2_X_KERNEL=tma keeps the patch kernel, =fold the LSU-fed one."""
-    return os.environ.get("HS2_X_KERNEL", "warp") == "warp" and nx == 512
+    """The warp-per-line x sweep (csrc/kernels_xw.cu) takes lines of 32 or 16 chunks of 16 cells (one or two
+    lines per warp); HS2_X_KERNEL=tma keeps the patch kernel, =fold the LSU-fed one."""
+    return os.environ.get("HS2_X_KERNEL", "warp") == "warp" and nx in (256, 512)
 
 
 def ghost_uniform_tables(lo, dg, hi, M, tol=1e-16):
@@ -487,7 +487,7 @@ class AdiPlan(object):
                     self._d_ucode[a] = torch.from_numpy(ucode).to(dev)
                     ax.h_utab = self._utab[a].ctypes.data
                     ax.d_ucode = self._d_ucode[a].data_ptr()
-                if a == 0 and x_warp_applies(self.shape[2]) and self.chunk[0] == (16, 32) and self.n_classes <= 64:
+                if a == 0 and x_warp_applies(self.shape[2]) and self.chunk[0] == (16, self.shape[2] // 16) and self.n_classes <= 64:
                     code, xw, xw_band = ghost_uniform_tables(*self.line_rows[0], 16)
                     self.d_xw_code = torch.from_numpy(code).to(dev)
                     self.d_xw_tab = torch.from_numpy(np.ascontiguousarray(xw)).to(dev)

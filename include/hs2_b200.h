@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS2_ABI_VERSION 4
+#define HS2_ABI_VERSION 5
 
 #define HS2_OK 0
 #define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
@@ -149,12 +149,70 @@ typedef struct hs2_source {
 int hs2_abi_version(void);
 const char *hs2_last_error(void);
 /* sizeof of the ABI structs as compiled (binding self-check): which = 0 hs2_axis_tables,
- * 1 hs2_plan_desc, 2 hs2_source; -1 for anything else                         */
+ * 1 hs2_plan_desc, 2 hs2_source, 3 hs2_build_desc, 4 hs2_axis_info; -1 for anything else */
 int hs2_sizeof(int which);
 
 /* replaces create_adi_step x3 + finalize (alternatingdirection_c.h:52,
  * alternatingdirection_c_pyx.pyx:212-282)                                     */
 int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out);
+/* The reference's C boundary builds a stage by itself: create_adi_step + one add_equation per cell
+ * (heatsim2/alternatingdirection_c.h:50-54, alternatingdirection_c.c:56-199), then tridiaglu
+ * (heatsim2/tridiag.pyx:9-43).  hs2_plan_build is that step here: from the per-cell class ids and the per-class
+ * coefficient rows alone it derives every table of hs2_plan_desc (unique lines per axis, Thomas factors,
+ * partitioned-solve tables, interface operators, the x kernels' extra tables) in native host and device code;
+ * the plan owns what it allocates.  No host-language table code is needed to drive the library.
+ *   h_class_coef  HOST [n_classes][8], as parsed from the equations, un-scaled:
+ *                 M = rho*c/dt, gx-, gx+, gy-, gy+, gz-, gz+ (face conductances), D (source weight)
+ *   chunk[a]      rows per chunk of the partitioned solve on axis a: 0 = choose, -1 = whole-line kernels only,
+ *                 8 / 16 / 32 = forced
+ *   utab_axes     bit a set: build the common-chunk table of axis a (h_utab / d_ucode)
+ *   d_class_id_global, nz_global, k0: z-slab of a larger grid (multi-GPU): the z tables describe the global lines
+ * Errors: HS2_E_INVALID with "Equation exceeds bounds of domain ..." where a conductance points out of the grid
+ * (the reference exits there, alternatingdirection_c.c:160-163).                                             */
+typedef struct hs2_build_desc {
+  int64_t nz, ny, nx;
+  int32_t n_classes;
+  int32_t class_id_bytes;        /* 1 (u8) or 2 (u16)                           */
+  const void *d_class_id;        /* device [nz][ny][nx]; must outlive the plan  */
+  const double *h_class_coef;    /* host [n_classes][8]                         */
+  int32_t device;
+  int32_t flags;                 /* HS2_FLAG_*                                  */
+  int32_t chunk[3];
+  int32_t utab_axes;
+  const void *d_class_id_global; /* device [nz_global][ny][nx] or NULL          */
+  int64_t nz_global, k0;
+} hs2_build_desc;
+int hs2_plan_build(const hs2_build_desc *desc, hs2_plan **out);
+
+/* what hs2_plan_build (or the caller of hs2_plan_create) chose for one axis    */
+typedef struct hs2_axis_info {
+  int64_t line_length, n_lines;
+  int32_t n_unique, chunk, n_chunks, pitch, band, xw_band;
+} hs2_axis_info;
+int hs2_plan_axis_info(const hs2_plan *plan, int axis, hs2_axis_info *info);
+
+/* Host copy of a table of a plan made by hs2_plan_build (inspection, tests, and the multi-GPU driver's set-up):
+ * returns the table's size in bytes (h_dst may be NULL to query it) or a negative error code.              */
+#define HS2_TAB_LINE_ID 0   /* u32 [n_lines]                        */
+#define HS2_TAB_ROWS_LO 1   /* f64 [n_unique][L] sub-diagonal       */
+#define HS2_TAB_ROWS_DG 2   /*                   diagonal           */
+#define HS2_TAB_ROWS_HI 3   /*                   super-diagonal     */
+#define HS2_TAB_LU 4        /* d_lu                                 */
+#define HS2_TAB_CHUNK 5     /* d_tab                                */
+#define HS2_TAB_GE 6        /* d_GE                                 */
+#define HS2_TAB_CHUNK_IL 7  /* d_tab_il                             */
+#define HS2_TAB_UTAB 8      /* h_utab                               */
+#define HS2_TAB_UCODE 9     /* d_ucode                              */
+#define HS2_TAB_XW 10       /* d_xw_tab                             */
+#define HS2_TAB_XW_CODE 11  /* d_xw_code                            */
+int64_t hs2_plan_copy_table(const hs2_plan *plan, int axis, int which, void *h_dst, int64_t capacity);
+
+/* The table algebra alone on host arrays (no device): unique lines lo/dg/hi [nu][L] -> tab [nu][5][pitch]
+ * (pitch = L rounded up to 4) and GE [nu][P][2P], P = ceil(L / M); ghost != 0: mirrored neighbours at both ends
+ * (d_xw_tab).  Returns the interface band (>= 0) or a negative error code.                                   */
+int hs2_tables_chunk(const double *lo, const double *dg, const double *hi, int nu, int L, int M, int ghost,
+                     double *tab, double *GE);
+
 /* replaces delete_adi_step (alternatingdirection_c.h:50)                      */
 int hs2_plan_destroy(hs2_plan *plan);
 /* number of kernels one hs2_step launches with this plan                     */

@@ -27,12 +27,15 @@ def test_library_exports_header_symbols():
 def test_struct_layout_matches_header():
     import ctypes
     from heatsim2_b200 import _cabi
-    # axis tables: 7 pointers + 6 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x4
-    assert ctypes.sizeof(_cabi.AxisTables) == 56 + 24
-    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 80 + 16
+    # axis tables: 9 pointers + 6 int32; desc: int64 x3, int32 x2, ptr x2, axis[3], int32 x4
+    assert ctypes.sizeof(_cabi.AxisTables) == 72 + 24
+    assert ctypes.sizeof(_cabi.PlanDesc) == 24 + 8 + 16 + 3 * 96 + 16
     assert ctypes.sizeof(_cabi.Source) == 24
+    # build desc: int64 x3, int32 x2, ptr x2, int32 x2, int32 x3 + int32, ptr, int64 x2
+    assert ctypes.sizeof(_cabi.BuildDesc) == 24 + 8 + 16 + 8 + 16 + 8 + 16
+    assert ctypes.sizeof(_cabi.AxisInfo) == 16 + 24
     L = _cabi.lib()
-    for which, struct in enumerate((_cabi.AxisTables, _cabi.PlanDesc, _cabi.Source)):
+    for which, struct in enumerate((_cabi.AxisTables, _cabi.PlanDesc, _cabi.Source, _cabi.BuildDesc, _cabi.AxisInfo)):
         assert L.hs2_sizeof(which) == ctypes.sizeof(struct)
 
 

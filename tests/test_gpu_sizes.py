@@ -61,7 +61,10 @@ LONG_LINES = [
     ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (16, 32), "x-warp"),
     ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-warp"),      # odd plane count, ragged row patches
     ("composite", dict(nz=19, ny=10, nx=512), 0, (16, 32), "x-warp"),
-    ("composite", dict(nz=19, ny=10, nx=256), 0, (16, 16), "x-tma"),
+    ("composite", dict(nz=19, ny=10, nx=256), 0, (16, 16), "x-warp"),          # two lines per warp
+    ("uniform_slab", dict(shape=(21, 47, 256)), 0, (16, 16), "x-warp"),
+    ("steelonfoam", dict(nz=12, ny=20, nx=256, nsteps=3), 0, (16, 16), "x-warp"),
+    ("steelonwater", dict(nz=9, ny=14, nx=128), 0, (16, 8), "x-tma"),
     ("steelonwater", dict(nz=8, ny=512, nx=16), 1, (32, 16), "tile-tma"),
     ("composite", dict(nz=512, ny=8, nx=16), 2, (32, 16), "tile-cpasync"),
     ("composite", dict(nz=1024, ny=8, nx=16), 2, (32, 32), "tile-cpasync-512"),
@@ -83,6 +86,7 @@ FOLD_LINES = [
 PATCH_LINES = [
     ("uniform_slab", dict(shape=(8, 16, 512)), 0, (16, 32), "x-tma"),
     ("steelonwater", dict(nz=9, ny=14, nx=512), 0, (16, 32), "x-tma"),
+    ("composite", dict(nz=19, ny=10, nx=256), 0, (16, 16), "x-tma"),
 ]
 
 
