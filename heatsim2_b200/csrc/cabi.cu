@@ -165,20 +165,33 @@ int hs2_sweep_z(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d
 
 int hs2_sweep_z_forward(hs2_plan *plan, double *d_work, double *d_Y, int64_t line0, int64_t n_lines, void *stream) {
   HS2_REQUIRE(plan && d_work && d_Y, "hs2_sweep_z_forward: NULL argument");
-  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, line0, n_lines, 0, nullptr, (cudaStream_t)stream);
+  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, line0, n_lines, 0, nullptr, false, (cudaStream_t)stream);
 }
 
 int hs2_sweep_z_forward_push(hs2_plan *plan, double *d_work, double *d_Y, int n_peers, const uint64_t *peer_Y,
                              void *stream) {
   HS2_REQUIRE(plan && d_work && d_Y, "hs2_sweep_z_forward_push: NULL argument");
-  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, 0, plan->d.ny * plan->d.nx, n_peers, peer_Y,
+  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, 0, plan->d.ny * plan->d.nx, n_peers, peer_Y, true,
+                   (cudaStream_t)stream);
+}
+
+int hs2_sweep_z_forward_push_cols(hs2_plan *plan, double *d_work, double *d_Y, int64_t line0, int64_t n_lines, int n_peers,
+                                  const uint64_t *peer_Y, void *stream) {
+  HS2_REQUIRE(plan && d_work && d_Y, "hs2_sweep_z_forward_push_cols: NULL argument");
+  return hs2_zdist(plan, 0, d_work, nullptr, nullptr, d_Y, line0, n_lines, n_peers, peer_Y, true, (cudaStream_t)stream);
+}
+
+int hs2_sweep_z_backward_cols(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const double *d_Yall,
+                              int64_t line0, int64_t n_lines, void *stream) {
+  HS2_REQUIRE(plan && d_T_in && d_T_out && d_work && d_Yall, "hs2_sweep_z_backward_cols: NULL argument");
+  return hs2_zdist(plan, 1, d_work, d_T_in, d_T_out, const_cast<double *>(d_Yall), line0, n_lines, 0, nullptr, true,
                    (cudaStream_t)stream);
 }
 
 int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const double *d_Yall,
                          int64_t line0, int64_t n_lines, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_T_out && d_work && d_Yall, "hs2_sweep_z_backward: NULL argument");
-  return hs2_zdist(plan, 1, d_work, d_T_in, d_T_out, const_cast<double *>(d_Yall), line0, n_lines, 0, nullptr,
+  return hs2_zdist(plan, 1, d_work, d_T_in, d_T_out, const_cast<double *>(d_Yall), line0, n_lines, 0, nullptr, false,
                    (cudaStream_t)stream);
 }
 

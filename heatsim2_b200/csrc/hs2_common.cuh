@@ -75,7 +75,7 @@ bool hs2_tile_supported(const hs2_plan *p, int axis);
 int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
-              int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st);
+              int64_t n_lines, int n_peers, const uint64_t *peer_y, bool full_cols, cudaStream_t st);
 // kernels_xt.cu - x sweep on TMA-staged patches (default where it applies); *done = false: fall through
 bool hs2_tile_xt_supported(const hs2_plan *p);
 int hs2_tile_sweep_xt(hs2_plan *p, const double *T, double *W, const hs2_source *src, const double *halo_lo,

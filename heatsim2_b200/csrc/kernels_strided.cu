@@ -437,7 +437,7 @@ template <int M, int W>
 __global__ void __launch_bounds__(256, 2)
 z_forward(const double *__restrict__ data, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
           double *__restrict__ Yloc, int pitch, int row0, int nz_loc, int64_t stride, int line0, int n_lines, int n_tiles,
-          ZPeers peers) {
+          ZPeers peers, int64_t ldy, int ycol0) {
   extern __shared__ __align__(16) double zsm[];
   double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
   const int w = threadIdx.x, p = threadIdx.y, g = threadIdx.z, G = blockDim.z;
@@ -471,14 +471,16 @@ z_forward(const double *__restrict__ data, const uint32_t *__restrict__ line_id,
       tg.pitch = pitch;
       yf = chunk_fwd<M, true>(v, tg, M, &last);
     }
-    Yloc[(int64_t)(2 * p) * n_lines + rel] = yf;
-    Yloc[(int64_t)(2 * p + 1) * n_lines + rel] = last;
+    // interface rows: [2 P][ldy], this launch's lines at columns ycol0 + rel
+    const int64_t y0 = (int64_t)(2 * p) * ldy + ycol0 + rel, y1 = y0 + ldy;
+    Yloc[y0] = yf;
+    Yloc[y1] = last;
     // the same two values straight into the memory of the slabs that need them (NVLink stores)
 #pragma unroll
     for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
       if (q < peers.n) {
-        peers.y[q][(int64_t)(2 * p) * n_lines + rel] = yf;
-        peers.y[q][(int64_t)(2 * p + 1) * n_lines + rel] = last;
+        peers.y[q][y0] = yf;
+        peers.y[q][y1] = last;
       }
     }
   }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(256, 2)
 z_backward(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
            const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
            const double *__restrict__ Yall, int pitch, int row0, int nz_loc, int P_glob, int chunk0, int band,
-           int64_t stride, int line0, int n_lines, int n_tiles) {
+           int64_t stride, int line0, int n_lines, int n_tiles, int64_t ldy, int ycol0) {
   extern __shared__ __align__(16) double zsm[];
   double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
   double *s_ge = s_tab + HS2_T_PLANES * nz_loc;          // [P_loc + 1][2 P_glob]: rows chunk0-1 .. chunk0+P_loc-1
@@ -523,14 +525,15 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
     for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
     // rows pg (-> E) and pg-1 (-> alpha) of the inverse interface operator
     double E = 0.0, alpha = 0.0;
+    const double *Yc = Yall + ycol0 + rel;               // this line's column of the interface rows [2 P_glob][ldy]
     {
       const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
       const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
       for (int q = q0; q <= q1; ++q) {
         const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
         const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
-        E = fma(g0, Yall[(int64_t)(2 * q) * n_lines + rel], E);
-        E = fma(g1, Yall[(int64_t)(2 * q + 1) * n_lines + rel], E);
+        E = fma(g0, Yc[(int64_t)(2 * q) * ldy], E);
+        E = fma(g1, Yc[(int64_t)(2 * q + 1) * ldy], E);
       }
       if (pg > 0) {
         const double *gm = ge - 2 * P_glob;
@@ -539,8 +542,8 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
         for (int q = a0; q <= a1; ++q) {
           const double g0 = tab_s ? TabShared::ld(gm_s, 2 * q) : __ldg(gm + 2 * q);
           const double g1 = tab_s ? TabShared::ld(gm_s, 2 * q + 1) : __ldg(gm + 2 * q + 1);
-          alpha = fma(g0, Yall[(int64_t)(2 * q) * n_lines + rel], alpha);
-          alpha = fma(g1, Yall[(int64_t)(2 * q + 1) * n_lines + rel], alpha);
+          alpha = fma(g0, Yc[(int64_t)(2 * q) * ldy], alpha);
+          alpha = fma(g1, Yc[(int64_t)(2 * q + 1) * ldy], alpha);
         }
       }
     }
@@ -574,7 +577,7 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
 
 template <int M, int W>
 int launch_zdist_w(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
-                   int n_lines, const ZPeers &peers, cudaStream_t st) {
+                   int n_lines, const ZPeers &peers, bool full_cols, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const hs2_axis_tables &ax = d.axis[2];
   const int P_loc = (int)(d.nz / M);
@@ -587,16 +590,19 @@ int launch_zdist_w(hs2_plan *pl, int phase, double *data, const double *Tin, dou
   int blocks = pl->sm_count * 2;
   if (blocks > (n_tiles + G - 1) / G) blocks = (n_tiles + G - 1) / G;
   dim3 block(W, P_loc, G);
+  // interface rows: one column per line of this launch, or (full_cols) per line of the slab
+  const int64_t ldy = full_cols ? d.ny * d.nx : n_lines;
+  const int ycol0 = full_cols ? line0 : 0;
   if (phase == 0) {
     auto kern = z_forward<M, W>;
     if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, block, smem, st>>>(data, ax.d_line_id, ax.d_tab, Y, ax.pitch, row0, nz_loc, d.ny * d.nx, line0, n_lines,
-                                      n_tiles, peers);
+                                      n_tiles, peers, ldy, ycol0);
   } else {
     auto kern = z_backward<M, W>;
     if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Y, ax.pitch, row0, nz_loc,
-                                      d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines, n_tiles);
+                                      d.z_chunks_global, d.z_chunk0, ax.band, d.ny * d.nx, line0, n_lines, n_tiles, ldy, ycol0);
   }
   HS2_CUDA_CHECK(cudaGetLastError());
   return HS2_OK;
@@ -604,15 +610,15 @@ int launch_zdist_w(hs2_plan *pl, int phase, double *data, const double *Tin, dou
 
 template <int M>
 int launch_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
-                 int n_lines, const ZPeers &peers, cudaStream_t st) {
+                 int n_lines, const ZPeers &peers, bool full_cols, cudaStream_t st) {
   const int P_loc = (int)(pl->d.nz / M);
   HS2_REQUIRE(P_loc * 8 <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
-  if (P_loc * 16 <= 256) return launch_zdist_w<M, 16>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, st);
-  return launch_zdist_w<M, 8>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, st);
+  if (P_loc * 16 <= 256) return launch_zdist_w<M, 16>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, full_cols, st);
+  return launch_zdist_w<M, 8>(pl, phase, data, Tin, Tout, Y, line0, n_lines, peers, full_cols, st);
 }
 
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
-              int64_t n_lines, int n_peers, const uint64_t *peer_y, cudaStream_t st) {
+              int64_t n_lines, int n_peers, const uint64_t *peer_y, bool full_cols, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const int M = d.axis[2].chunk;
   HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
@@ -627,9 +633,9 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
   peers.n = n_peers;
   for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;
   switch (M) {
-    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
-    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
-    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, st);
+    case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
+    case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
+    default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
   }
 }
 

@@ -58,19 +58,28 @@ struct XwMaps {
 };
 
 // (all shared-memory operands are 32-bit shared-window addresses)
-__device__ __forceinline__ void xw_tma_load(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c1, int c2) {
+__device__ __forceinline__ void xw_tma_load(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c1, int c2, int c3 = 0) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(c1), "r"(c2), "r"(0), "r"(bar)
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
 
-__device__ __forceinline__ void xw_tma_store(const CUtensorMap *map, uint32_t src, int c1, int c2) {
+__device__ __forceinline__ void xw_tma_store(const CUtensorMap *map, uint32_t src, int c1, int c2, int c3 = 0) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(0), "r"(c1), "r"(c2), "r"(0)
+               "r"(src), "r"(0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+
+__device__ __forceinline__ double xw_lds1(uint32_t a) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+  return r;
+}
+
+// barrier of the two warps that share a line (WPL = 2)
+__device__ __forceinline__ void xw_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ void xw_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -142,17 +151,23 @@ __device__ __forceinline__ void xw_decode(int t, const XwRanges &rg, int tiles_y
 }
 
 // XW_R rows per plane per patch, XW_G groups per block, LPW lines per warp: 1 (nx = 512, lane = chunk) or
-// 2 (nx = 256: the two half warps hold the same row of the patch's two planes)
-template <typename CID, int XW_R, int XW_G, int LPW>
-__global__ void __maxnreg__(XW_G * 2 * XW_R / LPW <= 16 ? 128 : 96)
+// 2 (nx = 256: the two half warps hold the same row of the patch's two planes), WPL warps per line: 1 or
+// 2 (nx = 1024: warp h of a line holds chunks 32 h .. 32 h + 31; what crosses the middle of the line - one x
+// neighbour each way, the interface values within the band, E of chunk 31 - goes through shared memory between
+// two barriers of the pair)
+template <typename CID, int XW_R, int XW_G, int LPW, int WPL>
+__global__ void __maxnreg__(XW_G * 2 * XW_R * WPL / LPW <= 16 ? 128 : 96)
 sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, const double *__restrict__ coef_g, int n_classes,
                 int has_halo_lo, int has_halo_hi, const uint32_t *__restrict__ line_id, const double *__restrict__ tab, int pitch,
                 const double *__restrict__ GE, int band_g, const double *__restrict__ xw_tab, const uint8_t *__restrict__ xw_code,
                 int n_slots, int ge_w, int nz, int ny, int tiles_y, int n_tiles, XwRanges rg) {
-  constexpr int P = 32 / LPW;                                        // chunks per line
+  static_assert(LPW == 1 || WPL == 1, "two lines per warp or two warps per line");
+  constexpr int PW = 32 / LPW;                                       // chunks of a line in one warp (shuffle width)
+  constexpr int P = PW * WPL;                                        // chunks per line
   constexpr int NX = P * XW_M;
   constexpr uint32_t ROW = P * 128;                                  // bytes per row
-  constexpr int WPG = 2 * XW_R / LPW;                                // warps per group
+  constexpr uint32_t PART = ROW / WPL;                               // bytes of a row one warp loads / stores
+  constexpr int WPG = 2 * XW_R * WPL / LPW;                          // warps per group
   constexpr int CR = xw_box_rows(XW_R);                              // rows per segment in a plane box (odd)
   constexpr uint32_t XW_CBOX = CR * ROW;                             // one plane's box
   constexpr uint32_t XW_GROUP = 2 * XW_CBOX + 2 * XW_R * ROW;
@@ -160,7 +175,9 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   double *s_hdr = reinterpret_cast<double *>(xsm + XW_G * XW_GROUP);               // [n_slots][XW_HDR]
   double2 *s_ge = reinterpret_cast<double2 *>(s_hdr + n_slots * XW_HDR);            // [n_slots][ge_w][P]
   double *cfs = reinterpret_cast<double *>(s_ge + n_slots * ge_w * P);               // [n_classes][8]
-  uint64_t *barC = reinterpret_cast<uint64_t *>(cfs + n_classes * HS2_COEF_STRIDE);  // [XW_G]
+  double2 *s_y = reinterpret_cast<double2 *>(cfs + n_classes * HS2_COEF_STRIDE);    // [XW_G][2 XW_R][P]   (WPL = 2)
+  double *s_e = reinterpret_cast<double *>(s_y + (WPL == 2 ? XW_G * 2 * XW_R * P : 0));   // [XW_G][2 XW_R]
+  uint64_t *barC = reinterpret_cast<uint64_t *>(s_e + (WPL == 2 ? XW_G * 2 * XW_R : 0));  // [XW_G]
   uint64_t *barZ = barC + XW_G;                                                      // [XW_G * WPG]
   int *cnt = reinterpret_cast<int *>(barZ + XW_G * WPG);                             // [XW_G]
   uint8_t *s_code = reinterpret_cast<uint8_t *>(cnt + XW_G);                         // [n_slots]
@@ -168,9 +185,11 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5;
   const int g = wrp / WPG, w = wrp % WPG;
-  const int pz = LPW == 1 ? w / XW_R : lane >> 4;       // plane of this lane's line within the patch
-  const int rw = LPW == 1 ? w % XW_R : w;               // row of this lane's line within the patch
-  const int p = lane & (P - 1);                         // chunk
+  const int lw = WPL == 2 ? w >> 1 : w;                 // LPW = 1: the warp's line within the group
+  const int hx = WPL == 2 ? w & 1 : 0;                  // WPL = 2: which half of the line
+  const int pz = LPW == 1 ? lw / XW_R : lane >> 4;      // plane of this lane's line within the patch
+  const int rw = LPW == 1 ? lw % XW_R : w;              // row of this lane's line within the patch
+  const int p = hx * 32 + (lane & (PW - 1));            // chunk
   const int n_groups = gridDim.x * XW_G;
 
   const uint32_t gb = smem_u32(xsm) + g * XW_GROUP;
@@ -244,7 +263,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   };
 
   int r = 0, k0 = 0, j0 = 0;
-  uint32_t idw[NIDW];
+  uint32_t idw[NIDW], idn[NIDW];
   uint32_t lid = 0, lidn = 0;
   if (t < n_tiles) {
     xw_decode<XW_R>(t, rg, tiles_y, &r, &k0, &j0);
@@ -269,19 +288,19 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
     if (lane == 0 && warp_ok) {
       if (stored) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous d1 has left the rows
       const int n_ok = LPW == 1 ? 1 : (k0 + 1 < k1r ? 2 : 1);
-      xw_expect_tx(bZ, n_ok * ROW);
+      xw_expect_tx(bZ, n_ok * PART);
 #pragma unroll
       for (int h = 0; h < LPW; ++h) {
         const int hz = LPW == 1 ? pz : h;
         if (h < n_ok) {
           const int zk = hz == 0 ? k0 - 1 : k0 + 2;
-          const uint32_t dst = gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW;
+          const uint32_t dst = gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW + hx * PART;
           if (zk < 0 && has_halo_lo)
-            xw_tma_load(dst, &tm.HloZ, bZ, j, 0);
+            xw_tma_load(dst, &tm.HloZ, bZ, j, 0, hx * 32);
           else if (zk >= nz && has_halo_hi)
-            xw_tma_load(dst, &tm.HhiZ, bZ, j, 0);
+            xw_tma_load(dst, &tm.HhiZ, bZ, j, 0, hx * 32);
           else
-            xw_tma_load(dst, &tm.Z, bZ, j, zk);
+            xw_tma_load(dst, &tm.Z, bZ, j, zk, hx * 32);
         }
       }
     }
@@ -301,47 +320,102 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         v[2 * u + 1] = c.y;
       }
       // x neighbours across the chunk ends (closed outer faces: conductance 0, any finite value)
-      double xl = xw_shfl_up<P>(v[XW_M - 1], 1);
-      double xr_end = xw_shfl_down<P>(v[0], 1);
+      double xl = xw_shfl_up<PW>(v[XW_M - 1], 1);
+      double xr_end = xw_shfl_down<PW>(v[0], 1);
+      if (WPL == 2) {
+        // across the middle of the line: the neighbouring chunk's end value sits in the same box
+        if (hx == 0 && lane == 31) {
+          const int l = CR * 32 + rw + 1;
+          xr_end = xw_lds1((pz == 0 ? sC0 : sC1) + l * 128 + ((l & 7) << 4));
+        }
+        if (hx == 1 && lane == 0) {
+          const int l = CR * 31 + rw + 1;
+          xl = xw_lds1((pz == 0 ? sC0 : sC1) + l * 128 + ((7 ^ (l & 7)) << 4) + 8);
+        }
+      }
       if (p == 0) xl = v[0];
       if (p == P - 1) xr_end = v[XW_M - 1];
-      // y and z neighbours are read one 16-byte unit ahead of the arithmetic (the loads keep their program order:
-      // volatile asm).  Coefficient sets: cell 0, cells 1..14 (class of cell 8), cell 15 - or, where a chunk has a
-      // class change inside (warp-uniform `slow`), one set per cell
-      double2 ym[2], yp[2], za[2];
-      ym[0] = xw_lds(rowC - 128 + kYm), yp[0] = xw_lds(rowC + 128 + kYp), za[0] = xw_lds(rowA + kC);
-      double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (u < 7) {
-          ym[(u + 1) & 1] = xw_lds(rowC - 128 + (((u + 1) << 4) ^ kYm));
-          yp[(u + 1) & 1] = xw_lds(rowC + 128 + (((u + 1) << 4) ^ kYp));
-          za[(u + 1) & 1] = xw_lds(rowA + (((u + 1) << 4) ^ kC));
+      if (!slow) {
+        // coefficient sets: cell 0, cells 1..14 (class of cell 8), cell 15.  y and z neighbours are read one
+        // 16-byte unit ahead of the arithmetic (the loads keep their program order: volatile asm)
+        const uint32_t q0 = coef_s + xw_cell_class<CID>(idw, 0) * (HS2_COEF_STRIDE * 8);
+        const uint32_t qd = coef_s + xw_cell_class<CID>(idw, 8) * (HS2_COEF_STRIDE * 8);
+        const uint32_t q15 = coef_s + xw_cell_class<CID>(idw, 15) * (HS2_COEF_STRIDE * 8);
+        double2 ym = xw_lds(rowC - 128 + kYm), yp = xw_lds(rowC + 128 + kYp), za = xw_lds(rowA + kC);
+        double cxm, cxp, cym, cyp, cA, cB;
+        {
+          const double2 a0 = xw_lds(q0), a1 = xw_lds(q0 + 16), a2 = xw_lds(q0 + 32);
+          cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+          cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
+          cB = cB0 = pz == 0 ? a2.x : a2.y;
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int e = 2 * u + c;
-          if (slow || e <= 1 || e == XW_M - 1) {
-            const uint32_t qq = coef_s + xw_cell_class<CID>(idw, (slow || e != 1) ? e : 8) * (HS2_COEF_STRIDE * 8);
-            const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
-            cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
-            cA = pz == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
-            cB = pz == 0 ? a2.x : a2.y;
-            if (e == 0) cB0 = cB;
-            if (e == 1) cBd = cB;
-            if (e == XW_M - 1) cB15 = cB;
+        for (int u = 0; u < 8; ++u) {
+          double2 ymn = ym, ypn = yp, zan = za;
+          if (u < 7) {
+            ymn = xw_lds(rowC - 128 + (((u + 1) << 4) ^ kYm));
+            ypn = xw_lds(rowC + 128 + (((u + 1) << 4) ^ kYp));
+            zan = xw_lds(rowA + (((u + 1) << 4) ^ kC));
           }
-          const double tt = v[e];
-          const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
-          const double2 m = ym[u & 1], q = yp[u & 1], z = za[u & 1];
-          double rr = cxm * (xl - tt);
-          rr = fma(cxp, xr - tt, rr);
-          rr = fma(cym, (c ? m.y : m.x) - tt, rr);
-          rr = fma(cyp, (c ? q.y : q.x) - tt, rr);
-          rr = fma(cA, (c ? z.y : z.x) - tt, rr);
-          rr = fma(-cB, tt, rr);             // the private row adds cB * z below
-          xl = tt;
-          v[e] = rr;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            if (e == 1 || e == XW_M - 1) {
+              const uint32_t qq = e == 1 ? qd : q15;
+              const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
+              cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+              cA = pz == 0 ? a2.y : a2.x;
+              cB = pz == 0 ? a2.x : a2.y;
+              if (e == 1)
+                cBd = cB;
+              else
+                cB15 = cB;
+            }
+            const double tt = v[e];
+            const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
+            double rr = cxm * (xl - tt);
+            rr = fma(cxp, xr - tt, rr);
+            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
+            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
+            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
+            rr = fma(-cB, tt, rr);             // the private row adds cB * z below
+            xl = tt;
+            v[e] = rr;
+          }
+          ym = ymn, yp = ypn, za = zan;
+        }
+      } else {
+        // a chunk of the warp has a class change inside: one coefficient set per cell
+        int last_id = -1;
+        double cxm = 0, cxp = 0, cym = 0, cyp = 0, cA = 0, cB = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 ym = xw_lds(rowC - 128 + ((u << 4) ^ kYm));
+          const double2 yp = xw_lds(rowC + 128 + ((u << 4) ^ kYp));
+          const double2 za = xw_lds(rowA + ((u << 4) ^ kC));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int idc = xw_cell_class<CID>(idw, e);
+            if (idc != last_id) {
+              const uint32_t qq = coef_s + idc * (HS2_COEF_STRIDE * 8);
+              const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
+              cxm = a0.x, cxp = a0.y, cym = a1.x, cyp = a1.y;
+              cA = pz == 0 ? a2.y : a2.x;
+              cB = pz == 0 ? a2.x : a2.y;
+              last_id = idc;
+            }
+            const double tt = v[e];
+            const double xr = e < XW_M - 1 ? v[e + 1] : xr_end;
+            double rr = cxm * (xl - tt);
+            rr = fma(cxp, xr - tt, rr);
+            rr = fma(cym, (c ? ym.y : ym.x) - tt, rr);
+            rr = fma(cyp, (c ? yp.y : yp.x) - tt, rr);
+            rr = fma(cA, (c ? za.y : za.x) - tt, rr);
+            rr = fma(-cB, tt, rr);
+            xl = tt;
+            v[e] = rr;
+          }
         }
       }
     }
@@ -355,38 +429,76 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         if (more) issue_C(t + n_groups);
       }
     }
+    if (more) fetch_ids(rn, k0n, j0n, idn, lidn);     // in flight during the solve
+
     if (warp_ok) {
       xw_wait(bZ, parZ);
       parZ ^= 1;
       // (LPW = 2, upper line absent: its private row was not loaded - it still holds finite values, the line's
       //  results are not stored)
+      if (!slow) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
-        double b0 = u == 0 ? cB0 : cBd, b1 = u == 7 ? cB15 : cBd;
-        if (slow) {
-          const double2 s0 = xw_lds(coef_s + xw_cell_class<CID>(idw, 2 * u) * (HS2_COEF_STRIDE * 8) + 32);
-          const double2 s1 = xw_lds(coef_s + xw_cell_class<CID>(idw, 2 * u + 1) * (HS2_COEF_STRIDE * 8) + 32);
-          b0 = pz == 0 ? s0.x : s0.y;
-          b1 = pz == 0 ? s1.x : s1.y;
+        for (int u = 0; u < 8; ++u) {
+          const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
+          v[2 * u] = fma(u == 0 ? cB0 : cBd, zb.x, v[2 * u]);
+          v[2 * u + 1] = fma(u == 7 ? cB15 : cBd, zb.y, v[2 * u + 1]);
         }
-        v[2 * u] = fma(b0, zb.x, v[2 * u]);
-        v[2 * u + 1] = fma(b1, zb.y, v[2 * u + 1]);
+      } else {
+        int last_id = -1;
+        double cB = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 zb = xw_lds(rowB + ((u << 4) ^ kB));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int idc = xw_cell_class<CID>(idw, e);
+            if (idc != last_id) {
+              const double2 a2 = xw_lds(coef_s + idc * (HS2_COEF_STRIDE * 8) + 32);
+              cB = pz == 0 ? a2.x : a2.y;
+              last_id = idc;
+            }
+            v[e] = fma(cB, c ? zb.y : zb.x, v[e]);
+          }
+        }
       }
 
-    }
-    // class ids and unique-line id of the next patch's line: in flight during the solve
-    if (more)
-      fetch_ids(rn, k0n, j0n, idw, lidn);
-    else
-      lidn = 0;
-    if (warp_ok) {
       // ------------------------------------------------ partitioned solve along x, interfaces by shuffle
       // an absent line (LPW = 2) borrows the other half warp's unique-line id: same code path, results dropped
       const uint32_t lid_o = LPW == 1 ? lid : __shfl_xor_sync(0xffffffffu, lid, 16);     // (all lanes take part)
       const uint32_t lid_e = line_ok ? lid : lid_o;
       const bool uni_l = lid_e < (uint32_t)n_slots && s_code[lid_e] != 0;
       const bool uni = LPW == 1 ? uni_l : __all_sync(0xffffffffu, uni_l);     // warp-uniform
+      // (y_first, y_last) of the chunks dl below / above this lane's: by shuffle inside the warp, through shared
+      // memory across the middle of a two-warp line (a lane without that neighbour gets a finite value: its
+      // interface coefficient is 0)
+      double2 *sy = s_y + (g * 2 * XW_R + lw) * P;
+      const int pair_id = 1 + g * 2 * XW_R + lw;
+      auto nbr = [&](double yf_, double last_, int dl, double &yu, double &lu, double &yd, double &ld) {
+        yu = xw_shfl_up<PW>(yf_, dl), lu = xw_shfl_up<PW>(last_, dl);
+        yd = xw_shfl_down<PW>(yf_, dl), ld = xw_shfl_down<PW>(last_, dl);
+        if (WPL == 2) {
+          if (hx == 1 && lane < dl && p - dl >= 0) {
+            const double2 t2 = sy[p - dl];
+            yu = t2.x, lu = t2.y;
+          }
+          if (hx == 0 && lane + dl > 31 && p + dl < P) {
+            const double2 t2 = sy[p + dl];
+            yd = t2.x, ld = t2.y;
+          }
+        }
+      };
+      // alpha = E of the chunk before this lane's
+      auto alpha_of = [&](double E) {
+        double al = xw_shfl_up<PW>(E, 1);
+        if (WPL == 2) {
+          if (hx == 0 && lane == 31) s_e[g * 2 * XW_R + lw] = E;
+          xw_pair_sync(pair_id);
+          if (hx == 1 && lane == 0) al = s_e[g * 2 * XW_R + lw];
+        }
+        if (p == 0) al = 0.0;
+        return al;
+      };
       if (uni) {
         TabShared ts;
         ts.a = smem_u32(s_hdr + lid_e * XW_HDR);
@@ -396,16 +508,21 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         const double2 *gr = s_ge + (int)lid_e * ge_w * P + p;            // [d][chunk]
         const double2 gc = gr[band_u * P];
         double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
+        if (WPL == 2) {
+          sy[p] = make_double2(yf, last);
+          xw_pair_sync(pair_id);
+        }
         for (int dl = 1; dl <= band_u; ++dl) {
           const double2 gu = gr[(band_u - dl) * P], gd = gr[(band_u + dl) * P];
-          e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
-          e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
-          e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
-          e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
+          double yu, lu, yd, ld;
+          nbr(yf, last, dl, yu, lu, yd, ld);
+          e0 = fma(gu.x, yu, e0);
+          e1 = fma(gu.y, lu, e1);
+          e2 = fma(gd.x, yd, e2);
+          e3 = fma(gd.y, ld, e3);
         }
         const double E = (e0 + e1) + (e2 + e3);
-        double alpha = xw_shfl_up<P>(E, 1);
-        if (p == 0) alpha = 0.0;
+        const double alpha = alpha_of(E);
         chunk_bwd<XW_M, true>(v, ts, XW_M, alpha, E);
         if (p == 0) {
           // first chunk: its ghost neighbour is its own first value F: x = a - F b, F = a_0 / (1 + b_0)
@@ -423,17 +540,22 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
         const double2 *grow = reinterpret_cast<const double2 *>(GE + ((int64_t)lid_e * P + p) * (2 * P));
         const double2 gc = grow[p];
         double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
+        if (WPL == 2) {
+          sy[p] = make_double2(yf, last);
+          xw_pair_sync(pair_id);
+        }
         for (int dl = 1; dl <= band_g; ++dl) {
           const double2 gu = p - dl >= 0 ? grow[p - dl] : make_double2(0.0, 0.0);
           const double2 gd = p + dl < P ? grow[p + dl] : make_double2(0.0, 0.0);
-          e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
-          e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
-          e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
-          e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
+          double yu, lu, yd, ld;
+          nbr(yf, last, dl, yu, lu, yd, ld);
+          e0 = fma(gu.x, yu, e0);
+          e1 = fma(gu.y, lu, e1);
+          e2 = fma(gd.x, yd, e2);
+          e3 = fma(gd.y, ld, e3);
         }
         const double E = (e0 + e1) + (e2 + e3);
-        double alpha = xw_shfl_up<P>(E, 1);
-        if (p == 0) alpha = 0.0;
+        const double alpha = alpha_of(E);
         chunk_bwd<XW_M, true>(v, tg, XW_M, alpha, E);
       }
 
@@ -449,7 +571,7 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
 #pragma unroll
         for (int h = 0; h < LPW; ++h) {
           const int hz = LPW == 1 ? pz : h;
-          if (k0 + hz < k1r) xw_tma_store(&tm.O, gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW, j, k0 + hz);
+          if (k0 + hz < k1r) xw_tma_store(&tm.O, gb + 2 * XW_CBOX + (hz * XW_R + rw) * ROW + hx * PART, j, k0 + hz, hx * 32);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -457,11 +579,13 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
     }
     r = rn, k0 = k0n, j0 = j0n;
     lid = lidn;
+#pragma unroll
+    for (int q = 0; q < NIDW; ++q) idw[q] = idn[q];
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-bool xw_encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int rows) {
+bool xw_encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int rows, int segs = 0) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -476,17 +600,17 @@ bool xw_encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int r
   const int S = nx / 16;
   cuuint64_t dims[4] = {16, (cuuint64_t)ny, (cuuint64_t)nzz, (cuuint64_t)S};
   cuuint64_t strides[3] = {(cuuint64_t)nx * 8, (cuuint64_t)ny * nx * 8, 128};
-  cuuint32_t box[4] = {16, (cuuint32_t)rows, 1, (cuuint32_t)S};
+  cuuint32_t box[4] = {16, (cuuint32_t)rows, 1, (cuuint32_t)(segs ? segs : S)};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, es,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename CID, int XW_R, int XW_G, int LPW>
+template <typename CID, int XW_R, int XW_G, int LPW, int WPL = 1>
 int launch_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, const double *halo_hi, int part,
               cudaStream_t st, bool *done) {
-  constexpr int P = 32 / LPW, WPG = 2 * XW_R / LPW;
+  constexpr int P = 32 * WPL / LPW, WPG = 2 * XW_R * WPL / LPW, SEG = P / WPL;
   constexpr uint32_t XW_GROUP = (2 * xw_box_rows(XW_R) + 2 * XW_R) * P * 128;
   *done = false;
   const hs2_plan_desc &d = p->d;
@@ -510,20 +634,22 @@ int launch_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, co
   if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
   XwMaps tm;
   memset(&tm, 0, sizeof(tm));
-  if (!xw_encode4(&tm.C, T, nx, ny, nz, xw_box_rows(XW_R)) || !xw_encode4(&tm.Z, T, nx, ny, nz, 1) || !xw_encode4(&tm.O, W, nx, ny, nz, 1))
+  if (!xw_encode4(&tm.C, T, nx, ny, nz, xw_box_rows(XW_R)) || !xw_encode4(&tm.Z, T, nx, ny, nz, 1, SEG) ||
+      !xw_encode4(&tm.O, W, nx, ny, nz, 1, SEG))
     return HS2_OK;
-  if (halo_lo && !xw_encode4(&tm.HloZ, halo_lo, nx, ny, 1, 1)) return HS2_OK;
-  if (halo_hi && (!xw_encode4(&tm.HhiC, halo_hi, nx, ny, 1, xw_box_rows(XW_R)) || !xw_encode4(&tm.HhiZ, halo_hi, nx, ny, 1, 1))) return HS2_OK;
+  if (halo_lo && !xw_encode4(&tm.HloZ, halo_lo, nx, ny, 1, 1, SEG)) return HS2_OK;
+  if (halo_hi && (!xw_encode4(&tm.HhiC, halo_hi, nx, ny, 1, xw_box_rows(XW_R)) || !xw_encode4(&tm.HhiZ, halo_hi, nx, ny, 1, 1, SEG)))
+    return HS2_OK;
   const int ge_w = 2 * ax.xw_band + 1;
   const size_t per_slot = (size_t)XW_HDR * 8 + (size_t)ge_w * P * 16 + 1;
   const size_t fixed = (size_t)XW_G * XW_GROUP + (size_t)d.n_classes * HS2_COEF_STRIDE * 8 +
-                       (size_t)(XW_G + XW_G * WPG) * 8 + XW_G * 4 + 64;
+                       (size_t)(XW_G + XW_G * WPG) * 8 + (WPL == 2 ? (size_t)XW_G * 2 * XW_R * (P * 16 + 8) : 0) + XW_G * 4 + 64;
   if (fixed + 1024 > (size_t)p->max_smem_optin) return HS2_OK;
   int n_slots = (int)(((size_t)p->max_smem_optin - 1024 - fixed) / per_slot);
   if (n_slots > ax.n_unique) n_slots = ax.n_unique;
   if (n_slots > 64) n_slots = 64;
   const size_t smem = fixed + (size_t)n_slots * per_slot;
-  auto kern = sweep_xw_kernel<CID, XW_R, XW_G, LPW>;
+  auto kern = sweep_xw_kernel<CID, XW_R, XW_G, LPW, WPL>;
   HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = p->sm_count;
   const int64_t need = (n_tiles + XW_G - 1) / XW_G;
@@ -547,6 +673,12 @@ int launch_xw_v(hs2_plan *p, const double *T, double *W, const double *halo_lo, 
   // (a scheduler's quarter of the register file holds 4 warps of 128 or 5 of 96 registers)
   const int shape = getenv("HS2_XW_SHAPE") ? atoi(getenv("HS2_XW_SHAPE")) : 42;
   if (p->d.nx == 256) return launch_xw<CID, 4, 4, 2>(p, T, W, halo_lo, halo_hi, part, st, done);   // 2 lines per warp
+  if (p->d.nx == 1024) {
+    // 2 warps per line, rows of 8 KB: patches of 2 x 1 rows (3-row boxes), two groups per block (8 warps);
+    // HS2_XW_SHAPE=13: three groups (12 warps) - measured slower (0.79 vs 0.76 ms on 128 x 1024 x 1024)
+    if (shape == 13) return launch_xw<CID, 1, 3, 1, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
+    return launch_xw<CID, 1, 2, 1, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
+  }
   if (shape == 52) return launch_xw<CID, 5, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
   if (shape == 33) return launch_xw<CID, 3, 3, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
   return launch_xw<CID, 4, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
@@ -559,7 +691,7 @@ bool hs2_tile_xw_supported(const hs2_plan *p) {
   const hs2_axis_tables &ax = d.axis[0];
   if (d.flags & (HS2_FLAG_FORCE_FALLBACK | HS2_FLAG_X_FOLD | HS2_FLAG_X_PATCH)) return false;
   if (ax.chunk != XW_M || !ax.d_tab || !ax.d_GE || ax.pitch <= 0 || !ax.d_xw_tab || !ax.d_xw_code || ax.xw_band < 0) return false;
-  if ((d.nx != 512 && d.nx != 256) || ax.n_chunks != d.nx / XW_M || d.n_classes > 64) return false;
+  if ((d.nx != 1024 && d.nx != 512 && d.nx != 256) || ax.n_chunks != d.nx / XW_M || d.n_classes > 64) return false;
   if (d.ny >= ((int64_t)1 << 30) || d.nz >= ((int64_t)1 << 30)) return false;
   if ((reinterpret_cast<uintptr_t>(d.d_class_id) & 15)) return false;
   return true;

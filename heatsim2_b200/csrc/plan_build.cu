@@ -392,8 +392,9 @@ static void bt_parallel(int n, const std::function<void(int)> &fn) {
 // Rows per chunk for a line of length L (same policy as heatsim2_b200/plan.py choose_chunk: M = 8 with up to 16
 // chunks, 16 or 32 with up to 32; the largest M <= pref with at least 4 chunks, else the largest valid one;
 // lines of 16..512 cells on the x axis, a multiple of 16: 16 (the TMA-fed x kernels).  0: whole-line fallback.
-static int bt_choose_chunk(int L, int axis, int pref, bool x_tma) {
+static int bt_choose_chunk(int L, int axis, int pref, bool x_tma, bool x_warp) {
   if (axis == 0 && x_tma && L % 16 == 0 && L >= 16 && L <= 512) return 16;
+  if (axis == 0 && x_warp && L == 1024) return 16;     // two warps per line (kernels_xw.cu)
   const int Ms[3] = {8, 16, 32}, caps[3] = {16, 32, 32};
   int best_good = 0, smallest = 0, first_valid = 0;
   for (int q = 0; q < 3; ++q) {
@@ -585,6 +586,7 @@ static int bt_build(const hs2_build_desc *b, hs2_owned *own, hs2_plan_desc *d) {
   d->flags = b->flags;
   d->z_chunk0 = d->z_chunks_global = 0;
   const bool x_tma = !(b->flags & HS2_FLAG_X_FOLD);
+  const bool x_warp = !(b->flags & (HS2_FLAG_X_FOLD | HS2_FLAG_X_PATCH)) && b->n_classes <= 64;
   for (int axis = 0; axis < 3; ++axis) {
     BtAxis &a = own->axis[axis];
     std::vector<int64_t> weight;
@@ -595,13 +597,13 @@ static int bt_build(const hs2_build_desc *b, hs2_owned *own, hs2_plan_desc *d) {
                              b->n_classes, a, own->h_line_id[axis], weight);
     if (rc) return rc;
     int M = b->chunk[axis];
-    if (M == 0) M = glob ? 0 : bt_choose_chunk(L, axis, 32, x_tma);
+    if (M == 0) M = glob ? 0 : bt_choose_chunk(L, axis, 32, x_tma, x_warp);
     if (M < 0) M = 0;
     HS2_REQUIRE(M == 0 || M == 8 || M == 16 || M == 32, "hs2_plan_build: chunk[%d] = %d (0, 8, 16 or 32)", axis, M);
     if (glob) HS2_REQUIRE(M > 0 && nz % M == 0, "hs2_plan_build: slab thickness %lld is not a multiple of the z chunk %d", (long long)nz, M);
     a.M = M;
     const bool utab = !glob && M > 0 && (b->utab_axes & (1 << axis));
-    const bool xw = axis == 0 && M == 16 && (nx == 512 || nx == 256) && b->n_classes <= 64 && !(b->flags & (HS2_FLAG_X_FOLD | HS2_FLAG_X_PATCH));
+    const bool xw = axis == 0 && M == 16 && (nx == 1024 || nx == 512 || nx == 256) && x_warp;
     HS2_REQUIRE(bt_axis_tables(a, weight, !glob, axis == 0 && M > 0, utab, xw), "hs2_plan_build: singular interface system on axis %d",
                 axis);
     hs2_axis_tables &t = d->axis[axis];

@@ -152,12 +152,11 @@ class DistPlan(object):
         self.k0 = plan.slab["k0"]
         self.chunk = plan.chunk[2][0]
         self.p_loc = plan.shape[0] // self.chunk
-        # slabs whose interface values this slab needs: chunk p uses chunks p-1-band .. p+band
-        self.band = interface_band(plan.chunk_tabs[2][1])
-        self.hops = -(-(self.band + 1) // self.p_loc)
+        self._band = None
         # pipelining pays once the exchange is large (measured: no gain at 2 ranks)
         self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "1" if self.world <= 2 else "2"))
         self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
+        self.p2p_ranges = int(os.environ.get("HS2_DIST_P2P_RANGES", "2"))       # line ranges of the peer-memory z sweep (1 or 2)
         self._bufs = {}
         self.use_p2p = os.environ.get("HS2_DIST_P2P", "1") != "0"
         # upper bound of a flag wait.  Ranks of one job drift apart by far more than a
@@ -166,6 +165,22 @@ class DistPlan(object):
         self.p2p_timeout = float(os.environ.get("HS2_DIST_TIMEOUT_S", "1800"))
         self._px = None
         self.profile = None          # list: when set, _step_p2p appends 7 CUDA events per step
+
+    @property
+    def band(self):
+        """half-width of the z interface operator in chunks: from the device plan once it exists (hs2_plan_build
+        computed it), from the numpy statement of the tables otherwise (CPU runs)"""
+        if self._band is None:
+            if self.plan._handle is not None:
+                self._band = int(self.plan.axis_info(2).band)
+            else:
+                self._band = interface_band(self.plan.chunk_tabs[2][1])
+        return self._band
+
+    @property
+    def hops(self):
+        """slabs whose interface values this slab needs: chunk p uses chunks p-1-band .. p+band"""
+        return -(-(self.band + 1) // self.p_loc)
 
     # ------------------------------------------------------------- buffers
     def _buf(self, name, shape, like):
@@ -255,21 +270,29 @@ class DistPlan(object):
         if ev: ev[2].record()
         _cabi.check(lib.hs2_sweep_y(self.plan._handle, work.data_ptr(), st))
         if ev: ev[3].record()
-        # z: eliminate the local chunks; their interface values go to every slab in reach
-        arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
-        _cabi.check(lib.hs2_sweep_z_forward_push(self.plan._handle, work.data_ptr(), px.y_rows_of(me, par, me), cnt, arr, st))
+        # z: eliminate the local chunks; their interface values go to every slab in reach.  Two ranges of lines:
+        # the wait for range 0's rows is covered by the elimination of range 1, the wait for range 1's rows by
+        # the back substitution of range 0 (flags of range i: slot 128 i + source slab)
+        n_lines = self.shape[1] * self.shape[2]
+        ranges = self._line_ranges(n_lines, self.p2p_ranges if self.world <= 120 else 1)
+        for i, (l0, nl) in enumerate(ranges):
+            arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
+            _cabi.check(lib.hs2_sweep_z_forward_push_cols(self.plan._handle, work.data_ptr(), px.y_rows_of(me, par, me), l0, nl,
+                                                          cnt, arr, st))
+            arr, cnt = _u64_list([px.base[r] + 8 * (128 * i + me) for r in px.peers])
+            _cabi.check(lib.hs2_flag_signal(arr, cnt, n, st))
         if ev: ev[4].record()
-        arr, cnt = _u64_list([px.base[r] + 8 * me for r in px.peers])
-        _cabi.check(lib.hs2_flag_signal(arr, cnt, n, st))
-        arr, cnt = _u64_list([own + 8 * r for r in px.peers])
-        _cabi.check(lib.hs2_flag_wait(arr, cnt, n, self.p2p_timeout, own + px.OFF_STATUS, st))
-        if ev: ev[5].record()
-        _cabi.check(lib.hs2_sweep_z_backward(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
-                                             px.y_virtual(me, par), 0, self.shape[1] * self.shape[2], st))
+        for i, (l0, nl) in enumerate(ranges):
+            arr, cnt = _u64_list([own + 8 * (128 * i + r) for r in px.peers])
+            _cabi.check(lib.hs2_flag_wait(arr, cnt, n, self.p2p_timeout, own + px.OFF_STATUS, st))
+            if ev and i == 0: ev[5].record()
+            _cabi.check(lib.hs2_sweep_z_backward_cols(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
+                                                      px.y_virtual(me, par), l0, nl, st))
         if ev: ev[6].record()
         return T_out
 
-    PHASES = ("halo_push+x_interior", "halo_wait+x_boundary", "y", "z_forward_push", "interface_wait", "z_backward")
+    PHASES = ("halo_push+x_interior", "halo_wait+x_boundary", "y", "z_forward_push", "interface_wait(range 0)",
+              "z_backward(+wait range 1)")
 
     def profile_ms(self):
         """mean milliseconds per phase over the profiled steps (synchronises)"""
@@ -314,9 +337,9 @@ class DistPlan(object):
                 req.wait()
         return halo_lo, halo_hi
 
-    def _line_ranges(self, n_lines):
+    def _line_ranges(self, n_lines, pipeline=None):
         """Split the z-lines into `pipeline` ranges (multiples of 16 lines)."""
-        parts = max(1, min(self.pipeline, n_lines // self.min_lines))
+        parts = max(1, min(self.pipeline if pipeline is None else pipeline, n_lines // self.min_lines))
         step = -(-n_lines // parts)
         step = -(-step // 16) * 16
         return [(l0, min(step, n_lines - l0)) for l0 in range(0, n_lines, step)]

@@ -67,10 +67,14 @@ def thomas_factors(lo, dg, hi):
 XW_HDR = 128          # doubles per unique line in front of its interface rows (hs2_axis_tables.d_xw_tab)
 
 
-def x_warp_applies(nx):
-    """The warp-per-line x sweep (csrc/kernels_xw.cu) takes lines of 32 or 16 chunks of 16 cells (one or two
-    lines per warp); HS2_X_KERNEL=tma keeps the patch kernel, =fold the LSU-fed one."""
-    return os.environ.get("HS2_X_KERNEL", "warp") == "warp" and nx in (256, 512)
+def x_warp_applies(nx, n_classes=None):
+    """The warp-per-line x sweep (csrc/kernels_xw.cu) takes lines of 16, 32 or 64 chunks of 16 cells (two lines
+    per warp, one, or two warps per line) and up to 64 equation classes; HS2_X_KERNEL=tma keeps the patch
+    kernel, =fold the LSU-fed one.  Lines of 1024 cells have no other kernel for 64 chunks of 16, so there the
+    class count decides the chunking too."""
+    if os.environ.get("HS2_X_KERNEL", "warp") != "warp":
+        return False
+    return nx in (256, 512) or (nx == 1024 and (n_classes is None or n_classes <= 64))
 
 
 def ghost_uniform_tables(lo, dg, hi, M, tol=1e-16):
@@ -161,7 +165,7 @@ def x_tma_applies(nx):
     return os.environ.get("HS2_X_KERNEL", "warp") != "fold" and nx % 16 == 0 and 16 <= nx <= 512
 
 
-def choose_chunk(L, axis=None):
+def choose_chunk(L, axis=None, n_classes=None):
     """Rows per chunk M and chunk count P for a line of length L.  The kernels
     hold M doubles per thread in registers and run P*W threads per tile
     (W = 16 or 8 adjacent lines): M=8 with up to 16 chunks, M=16 with up to 32,
@@ -170,7 +174,7 @@ def choose_chunk(L, axis=None):
     HS2_CHUNK_X for the x axis) with at least 4 chunks is taken, else the
     largest valid M.  (0, 0): too long for the register-tile kernels
     (whole-line fallback)."""
-    if axis == 0 and (x_tma_applies(L) or x_warp_applies(L)):
+    if axis == 0 and (x_tma_applies(L) or x_warp_applies(L, n_classes)):
         return 16, L // 16                 # kernels_xt.cu / kernels_xw.cu: one 128-byte segment per thread
     valid = [(M, -(-L // M)) for M, cap in ((8, 16), (16, 32), (32, 32)) if -(-L // M) <= cap]
     if not valid:
@@ -346,8 +350,9 @@ class AdiPlan(object):
             self._global_ids = gid
             self.class_id = gid[k0:k0 + nz].contiguous()
         self._setup_vol_elements = volumetric_elements
-        self._build_lines()
-        self._global_ids = None
+        if self.slab is None:
+            self._global_ids = None
+        self._np = None               # host (numpy) statement of the tables, built on first use: tests, emulation
         self._dev = None
         self._handle = None
         # HS2_FORCE_FALLBACK=1: run the whole-line global-memory kernels (testing aid)
@@ -387,19 +392,73 @@ class AdiPlan(object):
                                  "Are external boundaries set correctly?" % name)
 
     # ------------------------------------------------------- unique line tables
+    # The product path builds every table natively (hs2_plan_build, csrc/plan_build.cu).  What follows is the numpy
+    # statement of the same algebra: the tests compare the two, the CPU emulation of the multi-GPU solve and
+    # reference_matrices read it, and HS2_TABLES=numpy feeds it to hs2_plan_create for A/B runs.
+    @property
+    def scaled_coef(self):
+        cc = self.class_coef
+        cap = cc[:, M_]
+        out = np.zeros((self.n_classes, _cabi.HS2_COEF_STRIDE))
+        out[:, 0:6] = cc[:, GXM:GZP + 1] / cap[:, None]
+        out[:, 6] = cc[:, D_] / cap
+        out[:, 7] = cap
+        return out
+
+    @property
+    def chunk(self):
+        """(rows per chunk, chunks) of the partitioned solve per axis - policy only, no tables"""
+        if self._handle is not None:
+            return [(i.chunk, i.n_chunks) for i in (self.axis_info(a) for a in range(3))]
+        out = []
+        for axis in range(3):
+            if axis == 2 and self.slab is not None:
+                M = slab_chunk(self.shape[0])
+                out.append((M, self.slab["nz_global"] // M))
+            else:
+                out.append(choose_chunk(self.shape[2 - axis], axis, self.n_classes))
+        return out
+
+    def axis_info(self, axis):
+        """hs2_plan_axis_info of the device plan"""
+        info = _cabi.AxisInfo()
+        _cabi.check(_cabi.lib().hs2_plan_axis_info(self._handle, axis, ctypes.byref(info)))
+        return info
+
+    def copy_table(self, axis, which, dtype=np.float64):
+        """host copy of a table of the natively built plan (hs2_plan_copy_table), flat"""
+        lib = _cabi.lib()
+        n = int(lib.hs2_plan_copy_table(self._handle, axis, which, None, 0))
+        if n < 0:
+            _cabi.check(n)
+        out = np.empty(n // np.dtype(dtype).itemsize, dtype=dtype)
+        if n:
+            got = int(lib.hs2_plan_copy_table(self._handle, axis, which, out.ctypes.data, n))
+            if got < 0:
+                _cabi.check(got)
+        return out
+
+    def _tables_np(self):
+        if self._np is None:
+            self._np = self._build_lines()
+        return self._np
+
+    line_id = property(lambda self: self._tables_np()["line_id"])
+    line_lu = property(lambda self: self._tables_np()["line_lu"])
+    line_rows = property(lambda self: self._tables_np()["line_rows"])
+    chunk_tabs = property(lambda self: self._tables_np()["chunk_tabs"])
+
     def _build_lines(self):
         cc = self.class_coef
         cap = cc[:, M_]
-        self.scaled_coef = np.zeros((self.n_classes, _cabi.HS2_COEF_STRIDE))
-        self.scaled_coef[:, 0:6] = cc[:, GXM:GZP + 1] / cap[:, None]
-        self.scaled_coef[:, 6] = cc[:, D_] / cap
-        self.scaled_coef[:, 7] = cap
+        if self.slab is not None and self._global_ids is None:
+            raise RuntimeError("the global class ids of this slab plan were released after the native build")
 
         def as_int(cid):
             return (cid.to(torch.int32) & 0xFFFF) if cid.dtype == torch.int16 else cid
 
-        self.line_id, self.line_lu, self.line_rows = [], [], []
-        self.chunk, self.chunk_tabs = [], []
+        line_id, line_lu, line_rows, chunk_tabs = [], [], [], []
+        policy = self.chunk if self._handle is None else None
         for axis in range(3):
             gm, gp = _AXIS_G[axis]
             rows = np.stack([-0.5 * cc[:, gm] / cap, 1.0 + 0.5 * (cc[:, gm] + cc[:, gp]) / cap, -0.5 * cc[:, gp] / cap], axis=1)
@@ -409,17 +468,15 @@ class AdiPlan(object):
             sub_lut = torch.from_numpy(sub_of_class.astype(np.int64)).to(cid.device)
             lid, reps = _unique_lines(as_int(cid), sub_lut, axis, len(urows))
             lo, dg, hi = (urows[:, c][reps] for c in range(3))
-            self.line_id.append(lid)                       # int32 tensor [n_lines]
-            self.line_rows.append((lo, dg, hi))            # numpy [n_unique, L] each
+            line_id.append(lid)                       # int32 tensor [n_lines]
+            line_rows.append((lo, dg, hi))            # numpy [n_unique, L] each
             if axis == 2 and self.slab is not None:
-                rows_per_chunk = slab_chunk(self.shape[0])
-                n_chunks = dg.shape[1] // rows_per_chunk
-                self.line_lu.append(np.zeros((dg.shape[0], 1, _cabi.HS2_LU_STRIDE)))    # whole-line path unused
+                line_lu.append(np.zeros((dg.shape[0], 1, _cabi.HS2_LU_STRIDE)))    # whole-line path unused
             else:
-                rows_per_chunk, n_chunks = choose_chunk(dg.shape[1], axis)
-                self.line_lu.append(thomas_factors(lo, dg, hi))
-            self.chunk.append((rows_per_chunk, n_chunks))
-            self.chunk_tabs.append(chunk_factors(lo, dg, hi, rows_per_chunk) if rows_per_chunk else None)
+                line_lu.append(thomas_factors(lo, dg, hi))
+            rows_per_chunk = (policy if policy is not None else self.chunk)[axis][0]
+            chunk_tabs.append(chunk_factors(lo, dg, hi, rows_per_chunk) if rows_per_chunk else None)
+        return dict(line_id=line_id, line_lu=line_lu, line_rows=line_rows, chunk_tabs=chunk_tabs)
 
     @property
     def launches_per_step(self):
@@ -442,6 +499,8 @@ class AdiPlan(object):
 
     @property
     def n_unique(self):
+        if self._handle is not None:
+            return tuple(int(self.axis_info(a).n_unique) for a in range(3))
         return tuple(int(t.shape[0]) for t in self.line_lu)
 
     # ------------------------------------------------------------- device side
@@ -458,6 +517,9 @@ class AdiPlan(object):
         self._dev = dev
         self.d_class_id = self.class_id.to(dev)
         self.class_id = self.d_class_id            # keep a single copy
+        if os.environ.get("HS2_TABLES", "native") != "numpy":
+            return self._build_native(lib, dev)
+        chunk = self.chunk
         self.d_coef = torch.from_numpy(self.scaled_coef).to(dev)
         self.d_line_id = [t.to(dev).contiguous() for t in self.line_id]
         self.d_line_lu = [torch.from_numpy(t).to(dev).contiguous() for t in self.line_lu]
@@ -475,37 +537,74 @@ class AdiPlan(object):
             ax.d_line_id = self.d_line_id[a].data_ptr()
             ax.n_unique = self.d_line_lu[a].shape[0]
             ax.d_lu = self.d_line_lu[a].data_ptr()
-            ax.chunk, ax.n_chunks = self.chunk[a]
+            ax.chunk, ax.n_chunks = chunk[a]
             if self.d_chunk[a] is not None:
                 ax.d_tab, ax.d_GE = (t.data_ptr() for t in self.d_chunk[a])
                 ax.pitch = self.d_chunk[a][0].shape[2]
                 ax.band = interface_band(self.chunk_tabs[a][1])
                 if (not self.slab or a != 2) and "xyz"[a] in self.utab_axes:
-                    Mc, Pc = self.chunk[a]
+                    Mc, Pc = chunk[a]
                     utab, ucode = uniform_chunks(self.chunk_tabs[a][0], self.shape[2 - a], Mc, Pc, self.line_id[a])
                     self._utab[a] = np.ascontiguousarray(utab)                    # host, read by hs2_plan_create
                     self._d_ucode[a] = torch.from_numpy(ucode).to(dev)
                     ax.h_utab = self._utab[a].ctypes.data
                     ax.d_ucode = self._d_ucode[a].data_ptr()
-                if a == 0 and x_warp_applies(self.shape[2]) and self.chunk[0] == (16, self.shape[2] // 16) and self.n_classes <= 64:
+                if a == 0 and x_warp_applies(self.shape[2], self.n_classes) and chunk[0] == (16, self.shape[2] // 16) \
+                        and self.n_classes <= 64:
                     code, xw, xw_band = ghost_uniform_tables(*self.line_rows[0], 16)
                     self.d_xw_code = torch.from_numpy(code).to(dev)
                     self.d_xw_tab = torch.from_numpy(np.ascontiguousarray(xw)).to(dev)
                     ax.d_xw_code, ax.d_xw_tab, ax.xw_band = self.d_xw_code.data_ptr(), self.d_xw_tab.data_ptr(), xw_band
                 if a == 0:
-                    M, P = self.chunk[0]
+                    M, P = chunk[0]
                     self.d_tab_il = torch.from_numpy(interleave_chunks(self.chunk_tabs[0][0], self.shape[2], M, P)).to(dev)
                     ax.d_tab_il = self.d_tab_il.data_ptr()
         desc.device = dev.index
         desc.flags = self.flags
         if self.slab is not None:
-            desc.z_chunk0 = self.slab["k0"] // self.chunk[2][0]
-            desc.z_chunks_global = self.chunk[2][1]
+            desc.z_chunk0 = self.slab["k0"] // chunk[2][0]
+            desc.z_chunks_global = chunk[2][1]
         handle = ctypes.c_void_p()
         with torch.cuda.device(dev):
             _cabi.check(lib.hs2_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
         self._desc = desc
         self._handle = handle
+
+    def _build_native(self, lib, dev):
+        """hs2_plan_build: the library derives every table from the class ids and the class coefficient rows."""
+        b = _cabi.BuildDesc()
+        b.nz, b.ny, b.nx = self.shape
+        b.n_classes = self.n_classes
+        b.class_id_bytes = self.d_class_id.element_size()
+        b.d_class_id = self.d_class_id.data_ptr()
+        b.h_class_coef = self.class_coef.ctypes.data_as(_cabi.c_double_p)
+        b.device = dev.index
+        b.flags = self.flags
+        # rows per chunk: the library's own choice (0) unless the environment forces one
+        forced = any(k in os.environ for k in ("HS2_CHUNK", "HS2_CHUNK_X"))
+        policy = self.chunk
+        for a in range(3):
+            b.chunk[a] = (policy[a][0] or -1) if forced else 0
+        b.utab_axes = sum(1 << a for a in range(3) if "xyz"[a] in self.utab_axes)
+        gid = None
+        if self.slab is not None:
+            if self._global_ids is None:
+                raise RuntimeError("the global class ids of this slab plan were released")
+            gid = self._global_ids.to(dev)
+            b.d_class_id_global = gid.data_ptr()
+            b.nz_global, b.k0 = self.slab["nz_global"], self.slab["k0"]
+            b.chunk[2] = policy[2][0]
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(lib.hs2_plan_build(ctypes.byref(b), ctypes.byref(handle)))
+        self._handle = handle
+        self._desc = b
+        del gid
+        if self._np is None:
+            self._global_ids = None        # 1 byte per GLOBAL cell: not kept on a rank that never inspects the tables
+        got = [(i.chunk, i.n_chunks) for i in (self.axis_info(a) for a in range(3))]
+        if not forced and got != [tuple(c) for c in policy]:
+            raise AssertionError("chunk policy of plan.py %r and of hs2_plan_build %r differ" % (policy, got))
 
     def release(self):
         if self._handle is not None:

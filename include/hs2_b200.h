@@ -314,6 +314,13 @@ int hs2_peer_close(void *d_ptr);
 int hs2_peer_free(void *d_ptr);
 int hs2_sweep_z_forward_push(hs2_plan *plan, double *d_work, double *d_Y,
                              int n_peers, const uint64_t *peer_Y, void *stream);
+/* The same two halves on a RANGE of z-lines [line0, line0 + n_lines) with the interface rows addressed by the
+ * line's number in the slab (row pitch ny*nx doubles, as in the mailboxes): the peer-memory step pipelines
+ * forward(range 1) behind the wait for range 0's rows, and backward(range 0) behind the wait for range 1's. */
+int hs2_sweep_z_forward_push_cols(hs2_plan *plan, double *d_work, double *d_Y, int64_t line0, int64_t n_lines,
+                                  int n_peers, const uint64_t *peer_Y, void *stream);
+int hs2_sweep_z_backward_cols(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work,
+                              const double *d_Yall, int64_t line0, int64_t n_lines, void *stream);
 int hs2_flag_signal(const uint64_t *flag_ptrs, int n, uint64_t value, void *stream);
 int hs2_flag_wait(const uint64_t *flag_ptrs, int n, uint64_t value,
                   double timeout_s, int *d_status, void *stream);

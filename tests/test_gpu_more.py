@@ -159,5 +159,6 @@ def test_constant_bank_tables_are_bit_identical(hs, name, kwargs):
             del os.environ["HS2_UTAB_AXES"]
         else:
             os.environ["HS2_UTAB_AXES"] = old
-    assert all(u is not None and int(u.sum()) > 0 for u in plan._d_ucode), "no uniform chunks found"
+    from heatsim2_b200 import _cabi
+    assert all(int(plan.copy_table(a, _cabi.TAB_UCODE, np.uint8).sum()) > 0 for a in range(3)), "no uniform chunks found"
     assert np.array_equal(a, b)

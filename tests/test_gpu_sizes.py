@@ -54,7 +54,8 @@ LONG_LINES = [
     ("steelonfoam", dict(nz=12, ny=20, nx=512, nsteps=3), 0, (16, 32), "x-warp"),   # delamination gap: lines with a class change inside
     ("uniform_slab", dict(shape=(8, 512, 16)), 1, (32, 16), "tile-tma"),
     ("uniform_slab", dict(shape=(512, 8, 16)), 2, (32, 16), "tile-cpasync"),
-    ("uniform_slab", dict(shape=(8, 16, 1024)), 0, (32, 32), "x-fold"),
+    ("uniform_slab", dict(shape=(8, 16, 1024)), 0, (16, 64), "x-warp"),       # two warps per line
+    ("uniform_slab", dict(shape=(21, 47, 1024)), 0, (16, 64), "x-warp"),      # odd plane count, many patches per group
     ("uniform_slab", dict(shape=(8, 1024, 16)), 1, (32, 32), "tile-tma-512"),
     ("uniform_slab", dict(shape=(1024, 8, 16)), 2, (32, 32), "tile-cpasync-512"),
     # several unique lines along the long axis (material change, thin layer, delamination)
@@ -68,7 +69,10 @@ LONG_LINES = [
     ("steelonwater", dict(nz=8, ny=512, nx=16), 1, (32, 16), "tile-tma"),
     ("composite", dict(nz=512, ny=8, nx=16), 2, (32, 16), "tile-cpasync"),
     ("composite", dict(nz=1024, ny=8, nx=16), 2, (32, 32), "tile-cpasync-512"),
-    ("steelonwater", dict(nz=8, ny=16, nx=1024), 0, (32, 32), "x-fold"),
+    ("steelonwater", dict(nz=8, ny=16, nx=1024), 0, (16, 64), "x-warp"),       # lines that are not ghost-uniform: tables from global memory
+    ("steelonwater", dict(nz=9, ny=14, nx=1024), 0, (16, 64), "x-warp"),
+    ("composite", dict(nz=19, ny=10, nx=1024), 0, (16, 64), "x-warp"),
+    ("steelonfoam", dict(nz=12, ny=20, nx=1024, nsteps=3), 0, (16, 64), "x-warp"),   # class change inside chunks, also across the middle
     # the benchmark's own tile shape on all three axes at once would be 512^3; 3 x (two long axes) instead
     ("uniform_slab", dict(shape=(4, 512, 512)), 1, (32, 16), "tile-tma"),
     ("uniform_slab", dict(shape=(512, 4, 512)), 2, (32, 16), "tile-cpasync"),
@@ -79,6 +83,8 @@ LONG_LINES = [
 FOLD_LINES = [
     ("uniform_slab", dict(shape=(8, 16, 512)), 0, (32, 16), "x-fold"),
     ("steelonwater", dict(nz=8, ny=16, nx=512), 0, (32, 16), "x-fold"),
+    ("uniform_slab", dict(shape=(8, 16, 1024)), 0, (32, 32), "x-fold"),
+    ("steelonwater", dict(nz=8, ny=16, nx=1024), 0, (32, 32), "x-fold"),
 ]
 
 # the TMA-fed patch kernel (kernels_xt.cu) runs the steps with a volumetric source and the lines of 16..496 cells;
