@@ -25,15 +25,22 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, kwargs, nsteps, q, p2p):
+def _worker(rank, world, port, name, kwargs, nsteps, q, p2p, same_gpu=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["HS2_DIST_P2P"] = "1" if p2p else "0"
-    os.environ["HS2_DIST_TIMEOUT_S"] = "10"
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    os.environ["HS2_DIST_TIMEOUT_S"] = "30" if same_gpu else "10"
+    os.environ["HS2_DIST_MIN_LINES"] = "512"          # two line ranges in the peer-memory z sweep on these small grids
+    if same_gpu:
+        # every rank on GPU 0: the peer-memory transport (CUDA IPC mailboxes, flags, stores from the z kernel)
+        # works between processes of one device too; only the set-up plumbing needs a backend (gloo)
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import heatsim2_b200 as hs
         from heatsim2_b200 import dist as hdist
@@ -57,12 +64,12 @@ def _worker(rank, world, port, name, kwargs, nsteps, q, p2p):
         dist.destroy_process_group()
 
 
-def _run(world, name, kwargs, nsteps, p2p=True):
+def _run(world, name, kwargs, nsteps, p2p=True, same_gpu=False):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, p2p)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, p2p, same_gpu)) for r in range(world)]
     for p in procs:
         p.start()
     try:
@@ -87,12 +94,32 @@ def _run(world, name, kwargs, nsteps, p2p=True):
     ("uniform_slab", dict(shape=(128, 48, 64)), 4),
     ("composite", dict(nz=64, ny=32, nx=32, ply=8), 4),
     ("sources_demo", dict(nz=16, ny=10, nx=14), 6),
+    ("steelonwater", dict(nz=64, ny=24, nx=512), 3),        # warp x kernel in slabs (interior / boundary planes)
 ])
 def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
     import adi_oracle
     import heatsim2_b200 as hs
     world = min(_ngpu(), 4) if name == "uniform_slab" else 2
     got = _run(world, name, kwargs, nsteps, p2p)
+    prob = problems.ALL[name](hs, **kwargs)
+    one = util.run_b200(hs, prob, nsteps=nsteps)
+    assert util.relerr(got, one) <= 1e-13
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=nsteps)) <= 1e-12
+
+
+@pytest.mark.skipif(_ngpu() < 1, reason="needs a GPU")
+@pytest.mark.parametrize("world,name,kwargs,nsteps", [
+    (2, "steelonfoam", dict(nz=64, ny=40, nx=48), 4),
+    (4, "uniform_slab", dict(shape=(128, 48, 64)), 3),
+    (2, "sources_demo", dict(nz=16, ny=10, nx=14), 6),
+])
+def test_peer_memory_transport_between_processes_on_one_gpu(world, name, kwargs, nsteps):
+    """The mailbox / flag / step-parity protocol of the peer-memory transport (dist.py PeerExchange, peer.cu,
+    z_forward's stores into the peers' rows) with every rank a process on GPU 0 - runs on a one-GPU box.
+    The GPU time-slices between the processes, so a flag wait costs a time slice; a few steps are enough."""
+    import adi_oracle
+    import heatsim2_b200 as hs
+    got = _run(world, name, kwargs, nsteps, p2p=True, same_gpu=True)
     prob = problems.ALL[name](hs, **kwargs)
     one = util.run_b200(hs, prob, nsteps=nsteps)
     assert util.relerr(got, one) <= 1e-13
