@@ -575,6 +575,224 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused slab z sweep (peer-memory transport): forward elimination, exchange of the interface rows and back
+// substitution in ONE persistent kernel, so that the eliminated chunk never leaves the chip (z_forward +
+// z_backward read the increment twice: 32 instead of 24 B per cell) and no wait is exposed between two launches.
+// Per tile (the 256 threads' lines: W lines x G groups, all local chunks):
+//   forward elimination from registers; (y_first, y_last) stored into the own interface rows and straight into
+//   the peers' mailboxes (NVLink stores); barrier; ONE thread publishes "tile t of step n is there" to every peer
+//   (fence + release store at system scope, cumulative over the block's stores through the barrier);
+//   the eliminated chunk is parked in shared memory while the NEXT tile is eliminated and published;
+//   then one thread waits (bounded) for the peers' flags of the parked tile, the tile is swapped back into
+//   registers, interface rows are read from L2 (ld.cg: the peers wrote them), back substitution, T_in + increment.
+// A block handles its tiles in increasing order and never waits for a tile before it has published that tile and
+// the next one, so two slabs cannot wait for each other, whatever the number of resident blocks on either GPU.
+struct ZFlags {
+  int n;
+  unsigned long long *wait[HS2_MAX_Z_PEERS];   // in this GPU's mailbox: [n_iters] flags written by peer q
+  unsigned long long *sig[HS2_MAX_Z_PEERS];    // in peer q's mailbox: [n_iters] flags of this slab
+};
+
+template <int M, int W>
+__global__ void __launch_bounds__(256, 2)
+z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
+        const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
+        double *Yall, int pitch, int row0, int nz_loc, int P_glob, int chunk0, int band, int64_t stride, int n_lines,
+        int n_tiles, ZPeers peers, ZFlags fl, unsigned long long step, long long max_cycles, int *status) {
+  extern __shared__ __align__(16) double zsm[];
+  double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
+  double *s_ge = s_tab + HS2_T_PLANES * nz_loc;          // [P_loc + 1][2 P_glob]: rows chunk0-1 .. chunk0+P_loc-1
+  const int w = threadIdx.x, p = threadIdx.y, g = threadIdx.z, G = blockDim.z;
+  const int P_loc = blockDim.y;
+  double *s_park = s_ge + (P_loc + 1) * 2 * P_glob;      // [M][256]: the eliminated chunk of the tile that waits
+  const int tid = (g * P_loc + p) * W + w, nthr = W * P_loc * G;
+  int tile = blockIdx.x * G;
+  if (tile >= n_tiles) return;
+  const uint32_t lid_c = line_id[tile * W];
+  for (int e = tid; e < HS2_T_PLANES * nz_loc; e += nthr)
+    s_tab[e] = tab[((int64_t)lid_c * HS2_T_PLANES + e / nz_loc) * pitch + row0 + e % nz_loc];
+  for (int e = tid; e < (P_loc + 1) * 2 * P_glob; e += nthr) {
+    const int row = chunk0 - 1 + e / (2 * P_glob);
+    s_ge[e] = row >= 0 ? GE[((int64_t)lid_c * P_glob + row) * (2 * P_glob) + e % (2 * P_glob)] : 0.0;
+  }
+  __syncthreads();
+  const int pg = chunk0 + p;
+  TabShared ts;
+  ts.a = smem_u32(s_tab + p * M);
+  ts.pitch_b = (uint32_t)nz_loc * 8u;
+  const uint32_t ge_s = smem_u32(s_ge + (p + 1) * 2 * P_glob);
+  double *Yloc = Yall + (int64_t)(2 * chunk0) * n_lines;
+  double *park = s_park + tid;
+  const bool dead = *reinterpret_cast<volatile int *>(status) != 0;     // an earlier wait timed out: do not wait again
+
+  double v[M];
+  // eliminate the thread's chunk of tile t0 (kept in v) and publish the tile
+  auto forward = [&](int t0) {
+    const int rel = (t0 + g) * W + w;
+    const bool live = t0 + g < n_tiles && rel < n_lines;
+    if (live) {
+      const uint32_t lid = line_id[rel];
+      const double *ptr = data + rel + (int64_t)p * M * stride;
+#pragma unroll
+      for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
+      double yf, last;
+      if (lid == lid_c) {
+        yf = chunk_fwd<M, true>(v, ts, M, &last);
+      } else {
+        TabGlobal tg;
+        tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+        tg.pitch = pitch;
+        yf = chunk_fwd<M, true>(v, tg, M, &last);
+      }
+      const int64_t y0 = (int64_t)(2 * p) * n_lines + rel, y1 = y0 + n_lines;
+      Yloc[y0] = yf;
+      Yloc[y1] = last;
+#pragma unroll
+      for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
+        if (q < peers.n) {
+          peers.y[q][y0] = yf;
+          peers.y[q][y1] = last;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const int it = t0 / G;
+      for (int q = 0; q < fl.n; ++q) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl.sig[q] + it), "l"(step) : "memory");
+    }
+  };
+
+  forward(tile);
+#pragma unroll
+  for (int t = 0; t < M; ++t) park[t * 256] = v[t];
+  for (;;) {
+    const int next = tile + gridDim.x * G;
+    const bool has_next = next < n_tiles;
+    if (has_next) {
+      forward(next);
+#pragma unroll
+      for (int t = 0; t < M; ++t) {      // swap: the parked tile comes back, the new one is parked (own slots only)
+        const double x = park[t * 256];
+        park[t * 256] = v[t];
+        v[t] = x;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < M; ++t) v[t] = park[t * 256];
+    }
+    // the peers' rows of `tile`
+    if (tid == 0 && !dead) {
+      const int it = tile / G;
+      const long long t0c = clock64();
+      for (int q = 0; q < fl.n; ++q) {
+        for (;;) {
+          unsigned long long f;
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fl.wait[q] + it) : "memory");
+          if (f >= step) break;
+          if (clock64() - t0c > max_cycles) {
+            atomicExch(status, 1);
+            break;
+          }
+          __nanosleep(100);
+        }
+      }
+    }
+    __syncthreads();
+    const int rel = (tile + g) * W + w;
+    if (tile + g < n_tiles && rel < n_lines) {
+      const uint32_t lid = line_id[rel];
+      const bool tab_s = lid == lid_c;
+      const int64_t off = rel + (int64_t)p * M * stride;
+      double E = 0.0, alpha = 0.0;
+      const double *Yc = Yall + rel;
+      {
+        const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
+        const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
+        for (int q = q0; q <= q1; ++q) {
+          const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
+          const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
+          E = fma(g0, __ldcg(Yc + (int64_t)(2 * q) * n_lines), E);
+          E = fma(g1, __ldcg(Yc + (int64_t)(2 * q + 1) * n_lines), E);
+        }
+        if (pg > 0) {
+          const double *gm = ge - 2 * P_glob;
+          const uint32_t gm_s = ge_s - 16u * (uint32_t)P_glob;
+          const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
+          for (int q = a0; q <= a1; ++q) {
+            const double g0 = tab_s ? TabShared::ld(gm_s, 2 * q) : __ldg(gm + 2 * q);
+            const double g1 = tab_s ? TabShared::ld(gm_s, 2 * q + 1) : __ldg(gm + 2 * q + 1);
+            alpha = fma(g0, __ldcg(Yc + (int64_t)(2 * q) * n_lines), alpha);
+            alpha = fma(g1, __ldcg(Yc + (int64_t)(2 * q + 1) * n_lines), alpha);
+          }
+        }
+      }
+      if (tab_s) {
+        chunk_bwd<M, true>(v, ts, M, alpha, E);
+      } else {
+        TabGlobal tg;
+        tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+        tg.pitch = pitch;
+        chunk_bwd<M, true>(v, tg, M, alpha, E);
+      }
+      double tin[2][8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tin[0][q] = Tin[off + (int64_t)q * stride];
+#pragma unroll
+      for (int gb = 0; gb < M; gb += 8) {
+        if (gb + 8 < M) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tin[((gb >> 3) + 1) & 1][q] = Tin[off + (int64_t)(gb + 8 + q) * stride];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[(gb >> 3) & 1][q] + v[gb + q];
+      }
+    }
+    if (!has_next) break;
+    tile = next;
+  }
+}
+
+template <int M, int W>
+int launch_zfused_w(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers,
+                    const ZFlags &fl, unsigned long long step, double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
+  const hs2_plan_desc &d = pl->d;
+  const hs2_axis_tables &ax = d.axis[2];
+  const int P_loc = (int)(d.nz / M);
+  const int G = 256 / (W * P_loc) > 0 ? 256 / (W * P_loc) : 1;
+  if (tile_lines) {
+    *tile_lines = W * G;
+    return HS2_OK;
+  }
+  const int n_lines = (int)(d.ny * d.nx);
+  const int n_tiles = (n_lines + W - 1) / W;
+  const int row0 = d.z_chunk0 * M;
+  const int nz_loc = (int)d.nz;
+  const size_t smem = ((size_t)HS2_T_PLANES * nz_loc + (size_t)(P_loc + 1) * 2 * d.z_chunks_global + (size_t)M * 256) * sizeof(double);
+  HS2_REQUIRE(smem <= 110 * 1024, "fused z sweep: tables and the parked tile need %zu B of shared memory", smem);
+  auto kern = z_fused<M, W>;
+  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = pl->sm_count * 2;
+  if (blocks > (n_tiles + G - 1) / G) blocks = (n_tiles + G - 1) / G;
+  dim3 block(W, P_loc, G);
+  kern<<<blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Yall, ax.pitch, row0, nz_loc, d.z_chunks_global,
+                                    d.z_chunk0, ax.band, d.ny * d.nx, n_lines, n_tiles, peers, fl, step,
+                                    (long long)(timeout_s * 1.9e9), status);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  pl->last_kernel[2] = HS2_K_Z_SLAB;
+  return HS2_OK;
+}
+
+template <int M>
+int launch_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers, const ZFlags &fl,
+                  unsigned long long step, double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
+  const int P_loc = (int)(pl->d.nz / M);
+  HS2_REQUIRE(P_loc * 8 <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
+  if (P_loc * 16 <= 256) return launch_zfused_w<M, 16>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+  return launch_zfused_w<M, 8>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+}
+
 template <int M, int W>
 int launch_zdist_w(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int line0,
                    int n_lines, const ZPeers &peers, bool full_cols, cudaStream_t st) {
@@ -636,6 +854,36 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
     case 8: return launch_zdist<8>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
     case 16: return launch_zdist<16>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
     default: return launch_zdist<32>(pl, phase, data, Tin, Tout, Y, (int)line0, (int)n_lines, peers, full_cols, st);
+  }
+}
+
+// fused slab z sweep; tile_lines != NULL: only report the lines per tile (one flag per tile in the mailboxes)
+int hs2_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, int n_peers, const uint64_t *peer_y,
+               const uint64_t *wait_flags, const uint64_t *sig_flags, uint64_t step, double timeout_s, int *status,
+               int *tile_lines, cudaStream_t st) {
+  const hs2_plan_desc &d = pl->d;
+  const int M = d.axis[2].chunk;
+  HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
+  HS2_REQUIRE((M == 8 || M == 16 || M == 32) && d.nz % M == 0 && d.axis[2].d_tab && d.axis[2].d_GE,
+              "distributed z sweep needs chunk tables and nz (%lld) divisible by the chunk size (%d)", (long long)d.nz, M);
+  HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
+  ZPeers peers;
+  ZFlags fl;
+  peers.n = fl.n = 0;
+  if (!tile_lines) {
+    HS2_REQUIRE(n_peers >= 0 && n_peers <= HS2_MAX_Z_PEERS && (n_peers == 0 || (peer_y && wait_flags && sig_flags)) && status,
+                "fused z sweep: %d peers (max %d)", n_peers, HS2_MAX_Z_PEERS);
+    peers.n = fl.n = n_peers;
+    for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
+      peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;
+      fl.wait[q] = q < n_peers ? reinterpret_cast<unsigned long long *>(wait_flags[q]) : nullptr;
+      fl.sig[q] = q < n_peers ? reinterpret_cast<unsigned long long *>(sig_flags[q]) : nullptr;
+    }
+  }
+  switch (M) {
+    case 8: return launch_zfused<8>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+    case 16: return launch_zfused<16>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+    default: return launch_zfused<32>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
   }
 }
 

@@ -585,6 +585,476 @@ sweep_xw_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, 
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two lines per lane (nx = 512).  The profile of the kernel above (profiles/NOTES_r02.md) shows the L1 data pipe at
+// 87 %: of 327 shared-memory wavefronts per line 160 are the five stencil streams and ~100 the broadcast loads of
+// the chunk table (one wavefront per double whatever the width).  Here a warp owns row j of BOTH planes of the
+// patch, lane p holds chunk p of the two lines:
+//   * the in-patch z neighbour of one line is the centre value of the other - in registers (4 stencil streams
+//     instead of 5);
+//   * lines with the same unique-line id (all of them on the BASELINE grids) are solved together: every table
+//     value and interface coefficient is loaded once for two lines, and the two recurrences interleave
+//     (two independent DFMA chains per thread).
+// A group is XW_R warps; shared memory per group as above.
+template <int M>
+__device__ __forceinline__ void chunk_fwd2(double (&a)[M], double (&b)[M], const TabShared &tb, double *yfa, double *la,
+                                           double *yfb, double *lb) {
+  {
+    const uint32_t q = tb.plane(HS2_T_INV);
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+      const double x = TabShared::ld(q, t);
+      a[t] *= x;
+      b[t] *= x;
+    }
+  }
+  double pa = 0.0, pb = 0.0;
+  {
+    const uint32_t q = tb.plane(HS2_T_F);
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+      const double f = TabShared::ld(q, t);
+      pa = fma(-f, pa, a[t]);
+      pb = fma(-f, pb, b[t]);
+      a[t] = pa;
+      b[t] = pb;
+    }
+  }
+  *la = pa, *lb = pb;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  {
+    const uint32_t q = tb.plane(HS2_T_C);
+#pragma unroll
+    for (int t = 0; t < M; t += 2) {
+      const double c0 = TabShared::ld(q, t), c1 = TabShared::ld(q, t + 1);
+      a0 = fma(c0, a[t], a0);
+      a1 = fma(c1, a[t + 1], a1);
+      b0 = fma(c0, b[t], b0);
+      b1 = fma(c1, b[t + 1], b1);
+    }
+  }
+  *yfa = a0 + a1, *yfb = b0 + b1;
+}
+
+template <int M>
+__device__ __forceinline__ void chunk_bwd2(double (&a)[M], double (&b)[M], const TabShared &tb, double alpha_a, double Ea,
+                                           double alpha_b, double Eb) {
+  {
+    const uint32_t q = tb.plane(HS2_T_S);
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+      const double x = TabShared::ld(q, t);
+      a[t] = fma(-alpha_a, x, a[t]);
+      b[t] = fma(-alpha_b, x, b[t]);
+    }
+  }
+  const uint32_t q = tb.plane(HS2_T_CP);
+  double na = Ea, nb = Eb;
+#pragma unroll
+  for (int t = M - 1; t >= 0; --t) {
+    if (t < M - 1) {
+      const double x = TabShared::ld(q, t);
+      na = fma(-x, na, a[t]);
+      nb = fma(-x, nb, b[t]);
+    }
+    a[t] = na;
+    b[t] = nb;
+  }
+}
+
+template <typename CID, int XW_R, int XW_G>
+__global__ void __maxnreg__(255)
+sweep_xw2_kernel(const __grid_constant__ XwMaps tm, const CID *__restrict__ cid, const double *__restrict__ coef_g, int n_classes,
+                 int has_halo_lo, int has_halo_hi, const uint32_t *__restrict__ line_id, const double *__restrict__ tab, int pitch,
+                 const double *__restrict__ GE, int band_g, const double *__restrict__ xw_tab, const uint8_t *__restrict__ xw_code,
+                 int n_slots, int ge_w, int nz, int ny, int tiles_y, int n_tiles, XwRanges rg) {
+  constexpr int P = 32;
+  constexpr int NX = P * XW_M;
+  constexpr uint32_t ROW = P * 128;
+  constexpr int WPG = XW_R;                                          // warps per group: one per row of the patch
+  constexpr int CR = xw_box_rows(XW_R);
+  constexpr uint32_t XW_CBOX = CR * ROW;
+  constexpr uint32_t XW_GROUP = 2 * XW_CBOX + 2 * XW_R * ROW;
+  extern __shared__ __align__(1024) unsigned char xsm[];
+  double *s_hdr = reinterpret_cast<double *>(xsm + XW_G * XW_GROUP);               // [n_slots][XW_HDR]
+  double2 *s_ge = reinterpret_cast<double2 *>(s_hdr + n_slots * XW_HDR);            // [n_slots][ge_w][P]
+  double *cfs = reinterpret_cast<double *>(s_ge + n_slots * ge_w * P);               // [n_classes][8]
+  uint64_t *barC = reinterpret_cast<uint64_t *>(cfs + n_classes * HS2_COEF_STRIDE);  // [XW_G]
+  uint64_t *barZ = barC + XW_G;                                                      // [XW_G * WPG]
+  int *cnt = reinterpret_cast<int *>(barZ + XW_G * WPG);                             // [XW_G]
+  uint8_t *s_code = reinterpret_cast<uint8_t *>(cnt + XW_G);                         // [n_slots]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wrp = tid >> 5;
+  const int g = wrp / WPG, rw = wrp % WPG;
+  const int p = lane;
+  const int n_groups = gridDim.x * XW_G;
+
+  const uint32_t gb = smem_u32(xsm) + g * XW_GROUP;
+  const uint32_t sC0 = gb, sC1 = gb + XW_CBOX;
+  const uint32_t sZ0 = gb + 2 * XW_CBOX + rw * ROW, sZ1 = sZ0 + XW_R * ROW;    // private rows of the two lines
+  const uint32_t bC = smem_u32(barC + g), bZ = smem_u32(barZ + wrp);
+  const uint32_t coef_s = smem_u32(cfs);
+
+  if (tid == 0) {
+    for (int q = 0; q < XW_G; ++q) {
+      mbar_init(barC + q, 1);
+      cnt[q] = 0;
+    }
+    for (int q = 0; q < XW_G * WPG; ++q) mbar_init(barZ + q, 1);
+    fence_mbar_init();
+  }
+  {
+    const int64_t stride = XW_HDR + ge_w * P * 2;
+    for (int q = tid; q < n_slots * XW_HDR; q += blockDim.x) s_hdr[q] = xw_tab[(int64_t)(q / XW_HDR) * stride + q % XW_HDR];
+    for (int q = tid; q < n_slots * ge_w * P; q += blockDim.x) {
+      const int sl = q / (ge_w * P), e = q % (ge_w * P);
+      s_ge[q] = reinterpret_cast<const double2 *>(xw_tab + (int64_t)sl * stride + XW_HDR)[e];
+    }
+    for (int q = tid; q < n_slots; q += blockDim.x) s_code[q] = xw_code[q];
+    for (int q = tid; q < n_classes * HS2_COEF_STRIDE; q += blockDim.x) cfs[q] = coef_g[q];
+  }
+  __syncthreads();
+
+  auto issue_C = [&](int t) {
+    int r, k0, j0;
+    xw_decode<XW_R>(t, rg, tiles_y, &r, &k0, &j0);
+    xw_expect_tx(bC, 2 * XW_CBOX);
+    xw_tma_load(sC0, &tm.C, bC, j0 - 1, k0);
+    if (k0 + 1 >= nz && has_halo_hi)
+      xw_tma_load(sC1, &tm.HhiC, bC, j0 - 1, 0);
+    else
+      xw_tma_load(sC1, &tm.C, bC, j0 - 1, k0 + 1);
+  };
+
+  int t = blockIdx.x * XW_G + g;
+  if (t < n_tiles && rw == 0 && lane == 0) issue_C(t);
+
+  const int lc = CR * p + rw + 1;
+  const uint32_t row0 = sC0 + lc * 128, row1 = sC1 + lc * 128;
+  const uint32_t kC = (lc & 7) << 4, kYm = ((lc - 1) & 7) << 4, kYp = ((lc + 1) & 7) << 4;
+  const uint32_t rowB0 = sZ0 + p * 128, rowB1 = sZ1 + p * 128;
+  const uint32_t kB = (p & 7) << 4;
+
+  constexpr int NIDW = sizeof(CID) == 1 ? 4 : 8;
+  auto fetch_ids = [&](int rr, int kq, int jq, uint32_t (&ids)[NIDW], uint32_t &lid_out) {
+    lid_out = 0;
+    if (jq < ny && kq < (rr ? rg.k1[1] : rg.k1[0])) {
+      const uint4 *q4 = reinterpret_cast<const uint4 *>(cid + (((int64_t)kq * ny + jq) * NX + p * XW_M));
+      const uint4 a = __ldg(q4);
+      ids[0] = a.x, ids[1] = a.y, ids[2] = a.z, ids[3] = a.w;
+      if (sizeof(CID) == 2) {
+        const uint4 b = __ldg(q4 + 1);
+        ids[NIDW - 4] = b.x, ids[NIDW - 3] = b.y, ids[NIDW - 2] = b.z, ids[NIDW - 1] = b.w;
+      }
+      lid_out = __ldg(line_id + (int64_t)kq * ny + jq);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NIDW; ++q) ids[q] = 0;
+    }
+  };
+
+  int r = 0, k0 = 0, j0 = 0;
+  uint32_t ia[NIDW], ib[NIDW], na[NIDW], nb[NIDW];       // class ids of this lane's chunk: lines A (plane k0), B (k0+1); next patch
+  uint32_t lida = 0, lidb = 0, lidna = 0, lidnb = 0;
+  if (t < n_tiles) {
+    xw_decode<XW_R>(t, rg, tiles_y, &r, &k0, &j0);
+    fetch_ids(r, k0, j0 + rw, ia, lida);
+    fetch_ids(r, k0 + 1, j0 + rw, ib, lidb);
+  }
+  uint32_t parC = 0, parZ = 0;
+  bool stored = false;
+  const int band_u = (ge_w - 1) >> 1;
+
+  // coefficient set of class c as seen from plane z of the patch: (x-, x+, y-, y+, in-patch z, out-of-patch z)
+  struct Cf {
+    double xm, xp, ym, yp, zi, zo;
+  };
+  auto load_cf = [&](int c, int z) {
+    const uint32_t qq = coef_s + c * (HS2_COEF_STRIDE * 8);
+    const double2 a0 = xw_lds(qq), a1 = xw_lds(qq + 16), a2 = xw_lds(qq + 32);
+    Cf f;
+    f.xm = a0.x, f.xp = a0.y, f.ym = a1.x, f.yp = a1.y;
+    f.zi = z == 0 ? a2.y : a2.x;      // plane 0: z+ is in the patch, plane 1: z-
+    f.zo = z == 0 ? a2.x : a2.y;
+    return f;
+  };
+
+  for (; t < n_tiles; t += n_groups) {
+    const int j = j0 + rw;
+    const int k1r = r ? rg.k1[1] : rg.k1[0];
+    const bool ok_a = j < ny && k0 < k1r;                 // line A exists whenever the warp has work
+    const bool ok_b = j < ny && k0 + 1 < k1r;
+    const bool more = t + n_groups < n_tiles;
+    int rn = 0, k0n = 0, j0n = 0;
+    if (more) xw_decode<XW_R>(t + n_groups, rg, tiles_y, &rn, &k0n, &j0n);
+
+    // private rows: plane k0-1 for line A, plane k0+2 for line B (outside the grid: the neighbouring slab's halo
+    // plane, or zeros at a domain face)
+    if (lane == 0 && ok_a) {
+      if (stored) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      xw_expect_tx(bZ, (ok_b ? 2 : 1) * ROW);
+      if (k0 - 1 < 0 && has_halo_lo)
+        xw_tma_load(sZ0, &tm.HloZ, bZ, j, 0);
+      else
+        xw_tma_load(sZ0, &tm.Z, bZ, j, k0 - 1);
+      if (ok_b) {
+        if (k0 + 2 >= nz && has_halo_hi)
+          xw_tma_load(sZ1, &tm.HhiZ, bZ, j, 0);
+        else
+          xw_tma_load(sZ1, &tm.Z, bZ, j, k0 + 2);
+      }
+    }
+    xw_wait(bC, parC);
+    parC ^= 1;
+
+    double va[XW_M], vb[XW_M];
+    double oa0 = 0.0, oad = 0.0, oa15 = 0.0, ob0 = 0.0, obd = 0.0, ob15 = 0.0;     // out-of-patch z coefficients
+    bool slow = false;
+    if (ok_a) {
+      slow = __any_sync(0xffffffffu, !xw_interior_one_class<CID>(ia) || !xw_interior_one_class<CID>(ib));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double2 ca = xw_lds(row0 + ((u << 4) ^ kC)), cb = xw_lds(row1 + ((u << 4) ^ kC));
+        va[2 * u] = ca.x, va[2 * u + 1] = ca.y;
+        vb[2 * u] = cb.x, vb[2 * u + 1] = cb.y;
+      }
+      double xla = xw_shfl_up<P>(va[XW_M - 1], 1), xra_end = xw_shfl_down<P>(va[0], 1);
+      double xlb = xw_shfl_up<P>(vb[XW_M - 1], 1), xrb_end = xw_shfl_down<P>(vb[0], 1);
+      if (p == 0) xla = va[0], xlb = vb[0];
+      if (p == P - 1) xra_end = va[XW_M - 1], xrb_end = vb[XW_M - 1];
+      if (!slow) {
+        const int ca0 = xw_cell_class<CID>(ia, 0), cad = xw_cell_class<CID>(ia, 8), ca15 = xw_cell_class<CID>(ia, 15);
+        const int cb0 = xw_cell_class<CID>(ib, 0), cbd = xw_cell_class<CID>(ib, 8), cb15 = xw_cell_class<CID>(ib, 15);
+        Cf fa = load_cf(ca0, 0), fb = load_cf(cb0, 1);
+        oa0 = fa.zo, ob0 = fb.zo;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 yma = xw_lds(row0 - 128 + ((u << 4) ^ kYm)), ypa = xw_lds(row0 + 128 + ((u << 4) ^ kYp));
+          const double2 ymb = xw_lds(row1 - 128 + ((u << 4) ^ kYm)), ypb = xw_lds(row1 + 128 + ((u << 4) ^ kYp));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            if (e == 1) {
+              fa = load_cf(cad, 0), fb = load_cf(cbd, 1);
+              oad = fa.zo, obd = fb.zo;
+            }
+            if (e == XW_M - 1) {
+              fa = load_cf(ca15, 0), fb = load_cf(cb15, 1);
+              oa15 = fa.zo, ob15 = fb.zo;
+            }
+            const double ta = va[e], tb = vb[e];
+            const double xra = e < XW_M - 1 ? va[e + 1] : xra_end;
+            const double xrb = e < XW_M - 1 ? vb[e + 1] : xrb_end;
+            double ra = fa.xm * (xla - ta), rb = fb.xm * (xlb - tb);
+            ra = fma(fa.xp, xra - ta, ra), rb = fma(fb.xp, xrb - tb, rb);
+            ra = fma(fa.ym, (c ? yma.y : yma.x) - ta, ra), rb = fma(fb.ym, (c ? ymb.y : ymb.x) - tb, rb);
+            ra = fma(fa.yp, (c ? ypa.y : ypa.x) - ta, ra), rb = fma(fb.yp, (c ? ypb.y : ypb.x) - tb, rb);
+            ra = fma(fa.zi, tb - ta, ra), rb = fma(fb.zi, ta - tb, rb);
+            ra = fma(-fa.zo, ta, ra), rb = fma(-fb.zo, tb, rb);       // the private rows add zo * z below
+            xla = ta, xlb = tb;
+            va[e] = ra, vb[e] = rb;
+          }
+        }
+      } else {
+        // a chunk of the warp has a class change inside: one coefficient set per cell
+        int last_a = -1, last_b = -1;
+        Cf fa = {0, 0, 0, 0, 0, 0}, fb = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 yma = xw_lds(row0 - 128 + ((u << 4) ^ kYm)), ypa = xw_lds(row0 + 128 + ((u << 4) ^ kYp));
+          const double2 ymb = xw_lds(row1 - 128 + ((u << 4) ^ kYm)), ypb = xw_lds(row1 + 128 + ((u << 4) ^ kYp));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int ida = xw_cell_class<CID>(ia, e), idb = xw_cell_class<CID>(ib, e);
+            if (ida != last_a) fa = load_cf(ida, 0), last_a = ida;
+            if (idb != last_b) fb = load_cf(idb, 1), last_b = idb;
+            const double ta = va[e], tb = vb[e];
+            const double xra = e < XW_M - 1 ? va[e + 1] : xra_end;
+            const double xrb = e < XW_M - 1 ? vb[e + 1] : xrb_end;
+            double ra = fa.xm * (xla - ta), rb = fb.xm * (xlb - tb);
+            ra = fma(fa.xp, xra - ta, ra), rb = fma(fb.xp, xrb - tb, rb);
+            ra = fma(fa.ym, (c ? yma.y : yma.x) - ta, ra), rb = fma(fb.ym, (c ? ymb.y : ymb.x) - tb, rb);
+            ra = fma(fa.yp, (c ? ypa.y : ypa.x) - ta, ra), rb = fma(fb.yp, (c ? ypb.y : ypb.x) - tb, rb);
+            ra = fma(fa.zi, tb - ta, ra), rb = fma(fb.zi, ta - tb, rb);
+            ra = fma(-fa.zo, ta, ra), rb = fma(-fb.zo, tb, rb);
+            xla = ta, xlb = tb;
+            va[e] = ra, vb[e] = rb;
+          }
+        }
+      }
+    }
+    // this warp has read the shared boxes; the last of the group's warps to get here fetches the next patch
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const int old = atomicAdd(cnt + g, 1);
+      if (old == WPG - 1) {
+        atomicExch(cnt + g, 0);
+        if (more) issue_C(t + n_groups);
+      }
+    }
+    if (more) {      // in flight during the solve
+      fetch_ids(rn, k0n, j0n + rw, na, lidna);
+      fetch_ids(rn, k0n + 1, j0n + rw, nb, lidnb);
+    }
+
+    if (ok_a) {
+      xw_wait(bZ, parZ);
+      parZ ^= 1;
+      // (line B absent: its private row was not loaded - it still holds finite values, the line's results are not stored)
+      if (!slow) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 za = xw_lds(rowB0 + ((u << 4) ^ kB)), zb = xw_lds(rowB1 + ((u << 4) ^ kB));
+          va[2 * u] = fma(u == 0 ? oa0 : oad, za.x, va[2 * u]);
+          va[2 * u + 1] = fma(u == 7 ? oa15 : oad, za.y, va[2 * u + 1]);
+          vb[2 * u] = fma(u == 0 ? ob0 : obd, zb.x, vb[2 * u]);
+          vb[2 * u + 1] = fma(u == 7 ? ob15 : obd, zb.y, vb[2 * u + 1]);
+        }
+      } else {
+        int last_a = -1, last_b = -1;
+        double oa = 0, ob = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double2 za = xw_lds(rowB0 + ((u << 4) ^ kB)), zb = xw_lds(rowB1 + ((u << 4) ^ kB));
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int e = 2 * u + c;
+            const int ida = xw_cell_class<CID>(ia, e), idb = xw_cell_class<CID>(ib, e);
+            if (ida != last_a) oa = xw_lds(coef_s + ida * (HS2_COEF_STRIDE * 8) + 32).x, last_a = ida;
+            if (idb != last_b) ob = xw_lds(coef_s + idb * (HS2_COEF_STRIDE * 8) + 32).y, last_b = idb;
+            va[e] = fma(oa, c ? za.y : za.x, va[e]);
+            vb[e] = fma(ob, c ? zb.y : zb.x, vb[e]);
+          }
+        }
+      }
+
+      // ------------------------------------------------ partitioned solve along x, interfaces by shuffle
+      const uint32_t la_id = lida, lb_id = ok_b ? lidb : lida;       // an absent line B borrows A's tables (results dropped)
+      const bool uni_a = la_id < (uint32_t)n_slots && s_code[la_id] != 0;
+      const bool uni_b = lb_id < (uint32_t)n_slots && s_code[lb_id] != 0;
+      // one line with whatever tables it has
+      auto solve_one = [&](double (&v)[XW_M], uint32_t lid_e, bool uni) {
+        if (uni) {
+          TabShared ts;
+          ts.a = smem_u32(s_hdr + lid_e * XW_HDR);
+          ts.pitch_b = XW_M * 8u;
+          double last;
+          const double yf = chunk_fwd<XW_M, true>(v, ts, XW_M, &last);
+          const double2 *gr = s_ge + (int)lid_e * ge_w * P + p;
+          const double2 gc = gr[band_u * P];
+          double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
+          for (int dl = 1; dl <= band_u; ++dl) {
+            const double2 gu = gr[(band_u - dl) * P], gd = gr[(band_u + dl) * P];
+            e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
+            e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
+            e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
+            e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
+          }
+          const double E = (e0 + e1) + (e2 + e3);
+          double alpha = xw_shfl_up<P>(E, 1);
+          if (p == 0) alpha = 0.0;
+          chunk_bwd<XW_M, true>(v, ts, XW_M, alpha, E);
+          if (p == 0) {
+            const uint32_t qb = ts.plane(HS2_T_PLANES);
+            const double F = v[0] * TabShared::ld(ts.plane(HS2_T_PLANES + 1), 0);
+#pragma unroll
+            for (int q = 0; q < XW_M - 1; ++q) v[q] = fma(-F, TabShared::ld(qb, q), v[q]);
+          }
+        } else {
+          TabGlobal tg;
+          tg.b = tab + ((int64_t)lid_e * HS2_T_PLANES) * pitch + p * XW_M;
+          tg.pitch = pitch;
+          double last;
+          const double yf = chunk_fwd<XW_M, true>(v, tg, XW_M, &last);
+          const double2 *grow = reinterpret_cast<const double2 *>(GE + ((int64_t)lid_e * P + p) * (2 * P));
+          const double2 gc = grow[p];
+          double e0 = gc.x * yf, e1 = gc.y * last, e2 = 0.0, e3 = 0.0;
+          for (int dl = 1; dl <= band_g; ++dl) {
+            const double2 gu = p - dl >= 0 ? grow[p - dl] : make_double2(0.0, 0.0);
+            const double2 gd = p + dl < P ? grow[p + dl] : make_double2(0.0, 0.0);
+            e0 = fma(gu.x, xw_shfl_up<P>(yf, dl), e0);
+            e1 = fma(gu.y, xw_shfl_up<P>(last, dl), e1);
+            e2 = fma(gd.x, xw_shfl_down<P>(yf, dl), e2);
+            e3 = fma(gd.y, xw_shfl_down<P>(last, dl), e3);
+          }
+          const double E = (e0 + e1) + (e2 + e3);
+          double alpha = xw_shfl_up<P>(E, 1);
+          if (p == 0) alpha = 0.0;
+          chunk_bwd<XW_M, true>(v, tg, XW_M, alpha, E);
+        }
+      };
+      if (uni_a && la_id == lb_id) {
+        // both lines on one ghost-uniform table: every table value is loaded once for the two of them
+        TabShared ts;
+        ts.a = smem_u32(s_hdr + la_id * XW_HDR);
+        ts.pitch_b = XW_M * 8u;
+        double yfa, lsa, yfb, lsb;
+        chunk_fwd2<XW_M>(va, vb, ts, &yfa, &lsa, &yfb, &lsb);
+        const double2 *gr = s_ge + (int)la_id * ge_w * P + p;
+        const double2 gc = gr[band_u * P];
+        double a0 = gc.x * yfa, a1 = gc.y * lsa, a2 = 0.0, a3 = 0.0;
+        double b0 = gc.x * yfb, b1 = gc.y * lsb, b2 = 0.0, b3 = 0.0;
+        for (int dl = 1; dl <= band_u; ++dl) {
+          const double2 gu = gr[(band_u - dl) * P], gd = gr[(band_u + dl) * P];
+          a0 = fma(gu.x, xw_shfl_up<P>(yfa, dl), a0);
+          a1 = fma(gu.y, xw_shfl_up<P>(lsa, dl), a1);
+          a2 = fma(gd.x, xw_shfl_down<P>(yfa, dl), a2);
+          a3 = fma(gd.y, xw_shfl_down<P>(lsa, dl), a3);
+          b0 = fma(gu.x, xw_shfl_up<P>(yfb, dl), b0);
+          b1 = fma(gu.y, xw_shfl_up<P>(lsb, dl), b1);
+          b2 = fma(gd.x, xw_shfl_down<P>(yfb, dl), b2);
+          b3 = fma(gd.y, xw_shfl_down<P>(lsb, dl), b3);
+        }
+        const double Ea = (a0 + a1) + (a2 + a3), Eb = (b0 + b1) + (b2 + b3);
+        double ala = xw_shfl_up<P>(Ea, 1), alb = xw_shfl_up<P>(Eb, 1);
+        if (p == 0) ala = 0.0, alb = 0.0;
+        chunk_bwd2<XW_M>(va, vb, ts, ala, Ea, alb, Eb);
+        if (p == 0) {
+          const uint32_t qb = ts.plane(HS2_T_PLANES);
+          const double f1 = TabShared::ld(ts.plane(HS2_T_PLANES + 1), 0);
+          const double Fa = va[0] * f1, Fb = vb[0] * f1;
+#pragma unroll
+          for (int q = 0; q < XW_M - 1; ++q) {
+            const double x = TabShared::ld(qb, q);
+            va[q] = fma(-Fa, x, va[q]);
+            vb[q] = fma(-Fb, x, vb[q]);
+          }
+        }
+      } else {
+        solve_one(va, la_id, uni_a);
+        solve_one(vb, lb_id, uni_b);
+      }
+
+      // ------------------------------------------------ d1 over the private rows (same swizzle) -> bulk tensor stores
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowB0 + ((u << 4) ^ kB)), "d"(va[2 * u]), "d"(va[2 * u + 1]) : "memory");
+      if (ok_b) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowB1 + ((u << 4) ^ kB)), "d"(vb[2 * u]), "d"(vb[2 * u + 1]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        xw_tma_store(&tm.O, sZ0, j, k0);
+        if (ok_b) xw_tma_store(&tm.O, sZ1, j, k0 + 1);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      stored = true;
+    }
+    r = rn, k0 = k0n, j0 = j0n;
+    lida = lidna, lidb = lidnb;
+#pragma unroll
+    for (int q = 0; q < NIDW; ++q) ia[q] = na[q], ib[q] = nb[q];
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 bool xw_encode4(CUtensorMap *m, const void *base, int nx, int ny, int nzz, int rows, int segs = 0) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   static bool tried = false;
@@ -664,6 +1134,63 @@ int launch_xw(hs2_plan *p, const double *T, double *W, const double *halo_lo, co
   return HS2_OK;
 }
 
+template <typename CID, int XW_R, int XW_G>
+int launch_xw2(hs2_plan *p, const double *T, double *W, const double *halo_lo, const double *halo_hi, int part,
+              cudaStream_t st, bool *done) {
+  constexpr int P = 32, WPG = XW_R, SEG = P, WPL = 1;
+  constexpr uint32_t XW_GROUP = (2 * xw_box_rows(XW_R) + 2 * XW_R) * P * 128;
+  *done = false;
+  const hs2_plan_desc &d = p->d;
+  const hs2_axis_tables &ax = d.axis[0];
+  const int nx = (int)d.nx, ny = (int)d.ny, nz = (int)d.nz;
+  XwRanges rg;
+  if (part == 0) {
+    rg.n = 1, rg.k0[0] = 0, rg.k1[0] = nz, rg.k0[1] = rg.k1[1] = 0;
+  } else if (part == HS2_X_INTERIOR) {
+    rg.n = 1, rg.k0[0] = 1, rg.k1[0] = nz - 1, rg.k0[1] = rg.k1[1] = 0;
+  } else {
+    rg.n = 2, rg.k0[0] = 0, rg.k1[0] = 1, rg.k0[1] = nz - 1, rg.k1[1] = nz;
+  }
+  const int tiles_y = (ny + XW_R - 1) / XW_R;
+  int64_t n_tiles = 0;
+  for (int r = 0; r < rg.n; ++r) n_tiles += (int64_t)((rg.k1[r] - rg.k0[r] + 1) / 2) * tiles_y;
+  if (n_tiles <= 0) {
+    *done = true;
+    return HS2_OK;
+  }
+  if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
+  XwMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  if (!xw_encode4(&tm.C, T, nx, ny, nz, xw_box_rows(XW_R)) || !xw_encode4(&tm.Z, T, nx, ny, nz, 1, SEG) ||
+      !xw_encode4(&tm.O, W, nx, ny, nz, 1, SEG))
+    return HS2_OK;
+  if (halo_lo && !xw_encode4(&tm.HloZ, halo_lo, nx, ny, 1, 1, SEG)) return HS2_OK;
+  if (halo_hi && (!xw_encode4(&tm.HhiC, halo_hi, nx, ny, 1, xw_box_rows(XW_R)) || !xw_encode4(&tm.HhiZ, halo_hi, nx, ny, 1, 1, SEG)))
+    return HS2_OK;
+  const int ge_w = 2 * ax.xw_band + 1;
+  const size_t per_slot = (size_t)XW_HDR * 8 + (size_t)ge_w * P * 16 + 1;
+  const size_t fixed = (size_t)XW_G * XW_GROUP + (size_t)d.n_classes * HS2_COEF_STRIDE * 8 +
+                       (size_t)(XW_G + XW_G * WPG) * 8 + (WPL == 2 ? (size_t)XW_G * 2 * XW_R * (P * 16 + 8) : 0) + XW_G * 4 + 64;
+  if (fixed + 1024 > (size_t)p->max_smem_optin) return HS2_OK;
+  int n_slots = (int)(((size_t)p->max_smem_optin - 1024 - fixed) / per_slot);
+  if (n_slots > ax.n_unique) n_slots = ax.n_unique;
+  if (n_slots > 64) n_slots = 64;
+  const size_t smem = fixed + (size_t)n_slots * per_slot;
+  auto kern = sweep_xw2_kernel<CID, XW_R, XW_G>;
+  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = p->sm_count;
+  const int64_t need = (n_tiles + XW_G - 1) / XW_G;
+  if (blocks > need) blocks = need;
+  kern<<<(unsigned)blocks, XW_G * WPG * 32, smem, st>>>(tm, (const CID *)d.d_class_id, d.d_class_coef, d.n_classes,
+                                                        halo_lo ? 1 : 0, halo_hi ? 1 : 0, ax.d_line_id, ax.d_tab, ax.pitch, ax.d_GE,
+                                                        ax.band, ax.d_xw_tab, ax.d_xw_code, n_slots, ge_w, nz, ny, tiles_y,
+                                                        (int)n_tiles, rg);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  p->last_kernel[0] = HS2_K_X_WARP;
+  *done = true;
+  return HS2_OK;
+}
+
 template <typename CID>
 int launch_xw_v(hs2_plan *p, const double *T, double *W, const double *halo_lo, const double *halo_hi, int part,
                 cudaStream_t st, bool *done) {
@@ -671,7 +1198,7 @@ int launch_xw_v(hs2_plan *p, const double *T, double *W, const double *halo_lo, 
   //               52 = patches of 2 x 5 rows, two groups (20 warps, 96 registers),
   //               42 = patches of 2 x 4 rows (7-row boxes), two groups (16 warps, 128 registers)
   // (a scheduler's quarter of the register file holds 4 warps of 128 or 5 of 96 registers)
-  const int shape = getenv("HS2_XW_SHAPE") ? atoi(getenv("HS2_XW_SHAPE")) : 42;
+  const int shape = getenv("HS2_XW_SHAPE") ? atoi(getenv("HS2_XW_SHAPE")) : 24;
   if (p->d.nx == 256) return launch_xw<CID, 4, 4, 2>(p, T, W, halo_lo, halo_hi, part, st, done);   // 2 lines per warp
   if (p->d.nx == 1024) {
     // 2 warps per line, rows of 8 KB: patches of 2 x 1 rows (3-row boxes), two groups per block (8 warps);
@@ -679,6 +1206,9 @@ int launch_xw_v(hs2_plan *p, const double *T, double *W, const double *halo_lo, 
     if (shape == 13) return launch_xw<CID, 1, 3, 1, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
     return launch_xw<CID, 1, 2, 1, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
   }
+  // 24 (default): two lines per lane (sweep_xw2_kernel), patches of 2 x 4 rows, two groups per block (8 warps of
+  // 255 registers) - 0.524 ms at 512^3 against 0.561 for 42; 42 / 33 / 52: one line per lane
+  if (shape == 24) return launch_xw2<CID, 4, 2>(p, T, W, halo_lo, halo_hi, part, st, done);
   if (shape == 52) return launch_xw<CID, 5, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
   if (shape == 33) return launch_xw<CID, 3, 3, 1>(p, T, W, halo_lo, halo_hi, part, st, done);
   return launch_xw<CID, 4, 2, 1>(p, T, W, halo_lo, halo_hi, part, st, done);

@@ -64,7 +64,7 @@ class PeerExchange(object):
     HEADER = 4096
     OFF_FLAG_H_LO, OFF_FLAG_H_HI, OFF_STATUS = 2048, 2056, 3072
 
-    def __init__(self, rank, world, hops, p_loc, ny, nx, group, device):
+    def __init__(self, rank, world, hops, p_loc, ny, nx, group, device, n_tiles=0):
         self.rank, self.world, self.hops = rank, world, hops
         self.lib = _cabi.lib()
         self.peers = [r for d in range(1, hops + 1) for r in (rank - d, rank + d) if 0 <= r < world]
@@ -77,7 +77,10 @@ class PeerExchange(object):
         self.off_halo_lo = self.HEADER
         self.off_halo_hi = self.HEADER + self.plane_bytes
         self.off_y = [self.HEADER + 2 * self.plane_bytes + par * self.y_bytes for par in (0, 1)]
-        total = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
+        # per-tile flags of the fused z sweep: slot i holds the flags written by slab rank-hops+i (8 bytes per tile)
+        self.n_tiles = int(n_tiles)
+        self.off_tflag = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
+        total = self.off_tflag + (2 * hops + 1) * self.n_tiles * 8
         # every step below is collective: a failure on any rank (no IPC support, no
         # peer access) makes ALL ranks give up, so that they fall back to NCCL together
         ptr = ctypes.c_void_p()
@@ -116,6 +119,10 @@ class PeerExchange(object):
     def y_rows_of(self, r, parity, src):
         """where slab ``src``'s rows live in rank r's mailbox"""
         return self.y_virtual(r, parity) + src * self.slab_bytes
+
+    def tile_flags_of(self, r, src):
+        """where slab ``src``'s per-tile flags live in rank r's mailbox"""
+        return self.base[r] + self.off_tflag + (src - (r - self.hops)) * self.n_tiles * 8
 
     def status(self):
         out = torch.zeros(1, dtype=torch.int32)
@@ -157,6 +164,9 @@ class DistPlan(object):
         self.pipeline = int(os.environ.get("HS2_DIST_PIPELINE", "1" if self.world <= 2 else "2"))
         self.min_lines = int(os.environ.get("HS2_DIST_MIN_LINES", "4096"))
         self.p2p_ranges = int(os.environ.get("HS2_DIST_P2P_RANGES", "2"))       # line ranges of the peer-memory z sweep (1 or 2)
+        # one persistent kernel for the whole z sweep (forward, exchange through the mailboxes, backward);
+        # HS2_DIST_Z_FUSED=0: forward / flag / backward launches per line range
+        self.z_fused = os.environ.get("HS2_DIST_Z_FUSED", "1") != "0"
         self._bufs = {}
         self.use_p2p = os.environ.get("HS2_DIST_P2P", "1") != "0"
         # upper bound of a flag wait.  Ranks of one job drift apart by far more than a
@@ -225,7 +235,13 @@ class DistPlan(object):
         if self._px is None and self.use_p2p and T_in.is_cuda and self.world > 1:
             try:
                 ny, nx = self.shape[1:]
-                self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device)
+                n_tiles = 0
+                if self.z_fused:
+                    tl = int(_cabi.lib().hs2_sweep_z_fused_tile_lines(self.plan._handle))
+                    if tl <= 0:
+                        raise NotImplementedError("fused z sweep unavailable for this slab")
+                    n_tiles = -(-(ny * nx) // tl)
+                self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device, n_tiles)
             except NotImplementedError as exc:
                 self.use_p2p = False
                 self.p2p_unavailable = str(exc)
@@ -274,6 +290,16 @@ class DistPlan(object):
         # the wait for range 0's rows is covered by the elimination of range 1, the wait for range 1's rows by
         # the back substitution of range 0 (flags of range i: slot 128 i + source slab)
         n_lines = self.shape[1] * self.shape[2]
+        if self.z_fused:
+            y_arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
+            w_arr, _ = _u64_list([px.tile_flags_of(me, r) for r in px.peers])
+            s_arr, _ = _u64_list([px.tile_flags_of(r, me) for r in px.peers])
+            _cabi.check(lib.hs2_sweep_z_fused(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
+                                              px.y_virtual(me, par), cnt, y_arr, w_arr, s_arr, n, self.p2p_timeout,
+                                              own + px.OFF_STATUS, st))
+            if ev:
+                ev[4].record(); ev[5].record(); ev[6].record()
+            return T_out
         ranges = self._line_ranges(n_lines, self.p2p_ranges if self.world <= 120 else 1)
         for i, (l0, nl) in enumerate(ranges):
             arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
@@ -293,6 +319,17 @@ class DistPlan(object):
 
     PHASES = ("halo_push+x_interior", "halo_wait+x_boundary", "y", "z_forward_push", "interface_wait(range 0)",
               "z_backward(+wait range 1)")
+
+    def launches_per_step(self):
+        """kernels of this library one step of this rank launches (interior rank, no source)"""
+        n_lines = self.shape[1] * self.shape[2]
+        if self._px is not None and self.z_fused:
+            return 6       # flag signal (halo), x interior, flag wait, x boundary, y, fused z
+        if self._px is not None:
+            nr = len(self._line_ranges(n_lines, self.p2p_ranges if self.world <= 120 else 1))
+            # flag signal (halo), x interior, flag wait, x boundary, y, then per range: forward, signal, wait, backward
+            return 5 + 4 * nr
+        return 2 + 2 * len(self._line_ranges(n_lines))
 
     def profile_ms(self):
         """mean milliseconds per phase over the profiled steps (synchronises)"""

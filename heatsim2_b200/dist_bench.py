@@ -56,8 +56,10 @@ def run(args, shape, workload_name, clock_sampler=None):
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     _cabi.lib()
+    t_p = time.perf_counter()
+    prob = problems.uniform_slab(hs, shape=shape, random_T0=False)      # the caller's arrays (reference API): numpy, global grid
+    problem_s = time.perf_counter() - t_p
     t0 = time.perf_counter()
-    prob = problems.uniform_slab(hs, shape=shape, random_T0=False)
     P, S = hdist.setup(*prob["setup_args"])
     dplan = P.plan
     dplan.plan.ensure_device(dev)
@@ -139,6 +141,8 @@ def run(args, shape, workload_name, clock_sampler=None):
             it += 1
         phase_ms = dplan.profile_ms()
         dplan.profile = None
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, phase_ms)
     # e2e: every step each rank uploads its slab from pinned host memory and reads the result back
     H_in = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
     H_out = torch.empty(Ta.shape, dtype=torch.float64).pin_memory()
@@ -176,7 +180,8 @@ def run(args, shape, workload_name, clock_sampler=None):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(tuple(shape)), "grid": list(shape), "cells": n_global,
                            "cells_per_gpu": n_local, "decomposition": "z-slabs, %d planes per GPU" % (k1 - k0),
-                           "l2": "inputs larger than L2", "setup_s": setup_s, "finite": bool(int(finite))},
+                           "l2": "inputs larger than L2", "setup_s": setup_s, "problem_arrays_s": problem_s,
+                           "finite": bool(int(finite))},
                 "roofline": {"bound": "hbm", "kernel": "whole step (3 sweeps + z interface exchange)",
                              "achieved": 56 * n_local / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": 56 * n_local / (ms_step * 1e-3) / 1e9 / peak, "traffic": None,
@@ -185,13 +190,14 @@ def run(args, shape, workload_name, clock_sampler=None):
                 "comm": {"halo_bytes_per_rank_per_step": comm["halo_send"],
                          "interface_bytes_sent_per_rank_per_step": comm["interface_send"],
                          "interface_exchange": comm["interface_mode"], "rank0_phase_ms": phase_ms,
+                         "phase_ms_by_rank": all_phases,
                          "backend": ("CUDA IPC peer memory over NVLink (NCCL only for set-up)" if dplan._px is not None else
                                      "NCCL %s over NVLink" % ".".join(str(v) for v in torch.cuda.nccl.version()))},
                 "cpu_baseline": None,
                 "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_global * 8,
                         "d2h_bytes_per_step": n_global * 8, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "api": "per rank: pinned host slab -> device, heatsim2_b200.run_adi_steps (dist plan), device -> pinned host"},
-                "gpu_launches": args.steps * (8 if dplan._px is not None else 4) * world, "clocks": clocks}
+                "gpu_launches": args.steps * dplan.launches_per_step() * world, "clocks": clocks}
         print(json.dumps(line))
     dplan.check()
     dplan.close()

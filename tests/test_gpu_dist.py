@@ -25,13 +25,14 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, name, kwargs, nsteps, q, p2p, same_gpu=False):
+def _worker(rank, world, port, name, kwargs, nsteps, q, p2p, same_gpu=False, fused=True):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["HS2_DIST_P2P"] = "1" if p2p else "0"
     os.environ["HS2_DIST_TIMEOUT_S"] = "30" if same_gpu else "10"
+    os.environ["HS2_DIST_Z_FUSED"] = "1" if fused else "0"
     os.environ["HS2_DIST_MIN_LINES"] = "512"          # two line ranges in the peer-memory z sweep on these small grids
     if same_gpu:
         # every rank on GPU 0: the peer-memory transport (CUDA IPC mailboxes, flags, stores from the z kernel)
@@ -64,12 +65,12 @@ def _worker(rank, world, port, name, kwargs, nsteps, q, p2p, same_gpu=False):
         dist.destroy_process_group()
 
 
-def _run(world, name, kwargs, nsteps, p2p=True, same_gpu=False):
+def _run(world, name, kwargs, nsteps, p2p=True, same_gpu=False, fused=True):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, p2p, same_gpu)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, kwargs, nsteps, q, p2p, same_gpu, fused)) for r in range(world)]
     for p in procs:
         p.start()
     try:
@@ -88,7 +89,7 @@ def _run(world, name, kwargs, nsteps, p2p=True, same_gpu=False):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("p2p", [True, False], ids=["peer-memory", "nccl"])
+@pytest.mark.parametrize("p2p", [True, "ranges", False], ids=["peer-memory-fused", "peer-memory-ranges", "nccl"])
 @pytest.mark.parametrize("name,kwargs,nsteps", [
     ("steelonfoam", dict(nz=64, ny=40, nx=48), 6),
     ("uniform_slab", dict(shape=(128, 48, 64)), 4),
@@ -100,7 +101,7 @@ def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
     import adi_oracle
     import heatsim2_b200 as hs
     world = min(_ngpu(), 4) if name == "uniform_slab" else 2
-    got = _run(world, name, kwargs, nsteps, p2p)
+    got = _run(world, name, kwargs, nsteps, bool(p2p), fused=p2p is True)
     prob = problems.ALL[name](hs, **kwargs)
     one = util.run_b200(hs, prob, nsteps=nsteps)
     assert util.relerr(got, one) <= 1e-13
@@ -108,18 +109,21 @@ def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
 
 
 @pytest.mark.skipif(_ngpu() < 1, reason="needs a GPU")
-@pytest.mark.parametrize("world,name,kwargs,nsteps", [
-    (2, "steelonfoam", dict(nz=64, ny=40, nx=48), 4),
-    (4, "uniform_slab", dict(shape=(128, 48, 64)), 3),
-    (2, "sources_demo", dict(nz=16, ny=10, nx=14), 6),
+@pytest.mark.parametrize("world,name,kwargs,nsteps,fused", [
+    (2, "steelonfoam", dict(nz=64, ny=40, nx=48), 4, True),
+    (2, "steelonfoam", dict(nz=64, ny=40, nx=48), 4, False),
+    (4, "uniform_slab", dict(shape=(128, 48, 64)), 3, True),
+    (4, "uniform_slab", dict(shape=(128, 48, 64)), 3, False),
+    (2, "sources_demo", dict(nz=16, ny=10, nx=14), 6, True),
+    (2, "composite", dict(nz=64, ny=96, nx=128, ply=8), 3, True),      # 768 tiles: several per block, two line classes
 ])
-def test_peer_memory_transport_between_processes_on_one_gpu(world, name, kwargs, nsteps):
+def test_peer_memory_transport_between_processes_on_one_gpu(world, name, kwargs, nsteps, fused):
     """The mailbox / flag / step-parity protocol of the peer-memory transport (dist.py PeerExchange, peer.cu,
     z_forward's stores into the peers' rows) with every rank a process on GPU 0 - runs on a one-GPU box.
     The GPU time-slices between the processes, so a flag wait costs a time slice; a few steps are enough."""
     import adi_oracle
     import heatsim2_b200 as hs
-    got = _run(world, name, kwargs, nsteps, p2p=True, same_gpu=True)
+    got = _run(world, name, kwargs, nsteps, p2p=True, same_gpu=True, fused=fused)
     prob = problems.ALL[name](hs, **kwargs)
     one = util.run_b200(hs, prob, nsteps=nsteps)
     assert util.relerr(got, one) <= 1e-13

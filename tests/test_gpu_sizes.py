@@ -102,7 +102,7 @@ def test_patch_x_kernel_vs_oracle(hs, monkeypatch, name, kwargs, axis, chunk, ke
     test_long_lines_vs_oracle(hs, name, kwargs, axis, chunk, kernel)
 
 
-@pytest.mark.parametrize("shape", ["33", "52", "42"])
+@pytest.mark.parametrize("shape", ["33", "52", "42", "24"])
 def test_warp_x_kernel_shapes_vs_oracle(hs, shape):
     """both patch shapes of the warp-per-line kernel (HS2_XW_SHAPE is read once per process: subprocess)"""
     import os
@@ -110,11 +110,16 @@ def test_warp_x_kernel_shapes_vs_oracle(hs, shape):
     import sys
     code = ("import sys; sys.path[:0] = %r; import numpy as np, torch, heatsim2_b200 as hs, adi_oracle, problems, util\n"
             "for name, kw in (('uniform_slab', dict(shape=(21, 47, 512))), ('steelonwater', dict(nz=9, ny=14, nx=512)),\n"
-            "                 ('steelonfoam', dict(nz=12, ny=20, nx=512, nsteps=3))):\n"
+            "                 ('steelonfoam', dict(nz=12, ny=20, nx=512, nsteps=3)), ('composite', dict(nz=19, ny=10, nx=512)),\n"
+            "                 ('uniform_slab', dict(shape=(2, 5, 512))), ('uniform_slab', dict(shape=(1, 9, 512)))):\n"
             "    prob = problems.ALL[name](hs, **kw)\n"
             "    got = util.run_b200(hs, prob, nsteps=3)\n"
             "    err = util.relerr(got, adi_oracle.run(prob, nsteps=3))\n"
             "    assert err <= 3e-12, (name, err)\n"
+            "import slab_seq\n"
+            "prob = problems.ALL['steelonwater'](hs, nz=16, ny=14, nx=512)\n"       # interior / boundary plane ranges (slabs)
+            "err = util.relerr(slab_seq.run(hs, prob, 2, 3), adi_oracle.run(prob, nsteps=3))\n"
+            "assert err <= 3e-12, ('slabs', err)\n"
             "print('ok')\n") % ([p for p in sys.path if p],)
     env = dict(os.environ, HS2_XW_SHAPE=shape)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
