@@ -110,8 +110,8 @@ PROTOTYPES = {
     "hs2_sweep_z_backward_cols": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64,
                                                  ctypes.c_int64, c_void_p]),
     "hs2_sweep_z_fused": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int,
-                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
-                                         ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_double, c_void_p, c_void_p]),
+                                         ctypes.POINTER(ctypes.c_uint64), ctypes.c_double, c_void_p, c_void_p]),
+    "hs2_peer_fill_empty": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p]),
     "hs2_sweep_z_fused_tile_lines": (ctypes.c_int, [c_void_p]),
     "hs2_flag_signal": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_uint64, c_void_p]),
     "hs2_flag_wait": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_uint64, ctypes.c_double,

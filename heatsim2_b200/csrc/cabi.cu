@@ -196,18 +196,21 @@ int hs2_sweep_z_backward(hs2_plan *plan, const double *d_T_in, double *d_T_out, 
 }
 
 int hs2_sweep_z_fused(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, double *d_Yall, int n_peers,
-                      const uint64_t *peer_Y, const uint64_t *wait_flags, const uint64_t *signal_flags, uint64_t step,
-                      double timeout_s, int *d_status, void *stream) {
+                      const uint64_t *peer_Y, double timeout_s, int *d_status, void *stream) {
   HS2_REQUIRE(plan && d_T_in && d_T_out && d_work && d_Yall, "hs2_sweep_z_fused: NULL argument");
-  return hs2_zfused(plan, d_work, d_T_in, d_T_out, d_Yall, n_peers, peer_Y, wait_flags, signal_flags, step, timeout_s, d_status,
-                    nullptr, (cudaStream_t)stream);
+  return hs2_zfused(plan, d_work, d_T_in, d_T_out, d_Yall, n_peers, peer_Y, timeout_s, d_status, nullptr, (cudaStream_t)stream);
 }
 
 int hs2_sweep_z_fused_tile_lines(hs2_plan *plan) {
   if (!plan) return HS2_E_INVALID;
   int lines = 0;
-  int rc = hs2_zfused(plan, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0.0, nullptr, &lines, nullptr);
+  int rc = hs2_zfused(plan, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.0, nullptr, &lines, nullptr);
   return rc ? rc : lines;
+}
+
+int hs2_peer_fill_empty(void *d_ptr, int64_t n_doubles, void *stream) {
+  HS2_REQUIRE(d_ptr && n_doubles >= 0, "hs2_peer_fill_empty: bad argument");
+  return hs2_fill_empty(d_ptr, n_doubles, (cudaStream_t)stream);
 }
 
 int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, const hs2_source *src,

@@ -75,8 +75,8 @@ bool hs2_tile_supported(const hs2_plan *p, int axis);
 int hs2_tile_sweep_y(hs2_plan *p, double *W, cudaStream_t st);
 int hs2_tile_sweep_z(hs2_plan *p, const double *T, double *Tout, double *W, cudaStream_t st);
 int hs2_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, int n_peers, const uint64_t *peer_y,
-               const uint64_t *wait_flags, const uint64_t *sig_flags, uint64_t step, double timeout_s, int *status,
-               int *tile_lines, cudaStream_t st);
+               double timeout_s, int *status, int *tile_lines, cudaStream_t st);
+int hs2_fill_empty(void *d_ptr, int64_t n_doubles, cudaStream_t st);
 int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *Tout, double *Y, int64_t line0,
               int64_t n_lines, int n_peers, const uint64_t *peer_y, bool full_cols, cudaStream_t st);
 // kernels_xt.cu - x sweep on TMA-staged patches (default where it applies); *done = false: fall through

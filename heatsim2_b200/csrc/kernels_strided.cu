@@ -579,27 +579,33 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
 // Fused slab z sweep (peer-memory transport): forward elimination, exchange of the interface rows and back
 // substitution in ONE persistent kernel, so that the eliminated chunk never leaves the chip (z_forward +
 // z_backward read the increment twice: 32 instead of 24 B per cell) and no wait is exposed between two launches.
+//
+// The interface rows are their own flags: every slot of a mailbox holds HS2_Y_EMPTY (a NaN payload no arithmetic
+// produces) until the producing slab stores the value - one naturally aligned 8-byte store over NVLink, never torn -
+// and the consumer puts HS2_Y_EMPTY back once the block has read it (the rows are double-buffered by step parity and
+// a slab is never two steps ahead of a neighbour, dist.py).  No fence, no flag, no thread that publishes for the block.
+// (A first version with one flag per tile - barrier, fence.sys and release store by one thread, acquire spin by one
+// thread - ran at 1.4 ms per 512^3 slab against 0.84 ms for z_forward + z_backward: profiles/NOTES_r02.md.)
 // Per tile (the 256 threads' lines: W lines x G groups, all local chunks):
-//   forward elimination from registers; (y_first, y_last) stored into the own interface rows and straight into
-//   the peers' mailboxes (NVLink stores); barrier; ONE thread publishes "tile t of step n is there" to every peer
-//   (fence + release store at system scope, cumulative over the block's stores through the barrier);
-//   the eliminated chunk is parked in shared memory while the NEXT tile is eliminated and published;
-//   then one thread waits (bounded) for the peers' flags of the parked tile, the tile is swapped back into
-//   registers, interface rows are read from L2 (ld.cg: the peers wrote them), back substitution, T_in + increment.
-// A block handles its tiles in increasing order and never waits for a tile before it has published that tile and
-// the next one, so two slabs cannot wait for each other, whatever the number of resident blocks on either GPU.
-struct ZFlags {
-  int n;
-  unsigned long long *wait[HS2_MAX_Z_PEERS];   // in this GPU's mailbox: [n_iters] flags written by peer q
-  unsigned long long *sig[HS2_MAX_Z_PEERS];    // in peer q's mailbox: [n_iters] flags of this slab
-};
+//   forward elimination from registers; (y_first, y_last) stored into the own rows and straight into the peers'
+//   mailboxes; the eliminated chunk is parked in shared memory while the NEXT tile is eliminated and sent;
+//   then the tile comes back into registers, every thread reads the 2 (2 band + 2) interface values of its chunk
+//   from L2 (ld.cg), spinning (bounded) on the ones that are still empty; barrier; the peers' slots are emptied;
+//   back substitution, T_in + increment.
+// A block handles its tiles in increasing order and never waits for a tile before it has sent that tile and the
+// next one, so two slabs cannot wait for each other, whatever the number of resident blocks on either GPU.
+#define HS2_Y_EMPTY 0x7FF8DEADBEEF5A5Aull
+
+__global__ void fill_u64_kernel(unsigned long long *p, int64_t n, unsigned long long v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
 
 template <int M, int W>
 __global__ void __launch_bounds__(256, 2)
 z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
         const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
         double *Yall, int pitch, int row0, int nz_loc, int P_glob, int chunk0, int band, int64_t stride, int n_lines,
-        int n_tiles, ZPeers peers, ZFlags fl, unsigned long long step, long long max_cycles, int *status) {
+        int n_tiles, ZPeers peers, long long max_cycles, int *status) {
   extern __shared__ __align__(16) double zsm[];
   double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
   double *s_ge = s_tab + HS2_T_PLANES * nz_loc;          // [P_loc + 1][2 P_glob]: rows chunk0-1 .. chunk0+P_loc-1
@@ -624,14 +630,13 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
   const uint32_t ge_s = smem_u32(s_ge + (p + 1) * 2 * P_glob);
   double *Yloc = Yall + (int64_t)(2 * chunk0) * n_lines;
   double *park = s_park + tid;
-  const bool dead = *reinterpret_cast<volatile int *>(status) != 0;     // an earlier wait timed out: do not wait again
+  bool dead = *reinterpret_cast<volatile int *>(status) != 0;     // an earlier wait timed out: do not wait again
 
   double v[M];
-  // eliminate the thread's chunk of tile t0 (kept in v) and publish the tile
+  // eliminate the thread's chunk of tile t0 (kept in v); its interface values go to the own rows and to the peers
   auto forward = [&](int t0) {
     const int rel = (t0 + g) * W + w;
-    const bool live = t0 + g < n_tiles && rel < n_lines;
-    if (live) {
+    if (t0 + g < n_tiles && rel < n_lines) {
       const uint32_t lid = line_id[rel];
       const double *ptr = data + rel + (int64_t)p * M * stride;
 #pragma unroll
@@ -656,12 +661,23 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
         }
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      const int it = t0 / G;
-      for (int q = 0; q < fl.n; ++q) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl.sig[q] + it), "l"(step) : "memory");
+  };
+  // one interface value: own rows are ordered by the block barrier, a peer's slot is read until it is no longer empty
+  const long long t_begin = clock64();
+  auto y_get = [&](const double *q, bool own) {
+    double x = __ldcg(q);
+    if (!own && !dead) {
+      while (__double_as_longlong(x) == (long long)HS2_Y_EMPTY) {
+        if (clock64() - t_begin > max_cycles) {
+          atomicExch(status, 1);
+          dead = true;
+          break;
+        }
+        __nanosleep(64);
+        x = __ldcg(q);
+      }
     }
+    return x;
   };
 
   forward(tile);
@@ -682,53 +698,49 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
 #pragma unroll
       for (int t = 0; t < M; ++t) v[t] = park[t * 256];
     }
-    // the peers' rows of `tile`
-    if (tid == 0 && !dead) {
-      const int it = tile / G;
-      const long long t0c = clock64();
-      for (int q = 0; q < fl.n; ++q) {
-        for (;;) {
-          unsigned long long f;
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fl.wait[q] + it) : "memory");
-          if (f >= step) break;
-          if (clock64() - t0c > max_cycles) {
-            atomicExch(status, 1);
-            break;
-          }
-          __nanosleep(100);
+    __syncthreads();                     // the block's own rows of `tile` are there
+    const int rel = (tile + g) * W + w;
+    const bool live = tile + g < n_tiles && rel < n_lines;
+    uint32_t lid = 0;
+    double E = 0.0, alpha = 0.0;
+    double *Yc = Yall + rel;
+    if (live) {
+      lid = line_id[rel];
+      const bool tab_s = lid == lid_c;
+      const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
+      const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
+      for (int q = q0; q <= q1; ++q) {
+        const bool own = q >= chunk0 && q < chunk0 + P_loc;
+        const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
+        const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
+        E = fma(g0, y_get(Yc + (int64_t)(2 * q) * n_lines, own), E);
+        E = fma(g1, y_get(Yc + (int64_t)(2 * q + 1) * n_lines, own), E);
+      }
+      if (pg > 0) {
+        const double *gm = ge - 2 * P_glob;
+        const uint32_t gm_s = ge_s - 16u * (uint32_t)P_glob;
+        const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
+        for (int q = a0; q <= a1; ++q) {
+          const bool own = q >= chunk0 && q < chunk0 + P_loc;
+          const double g0 = tab_s ? TabShared::ld(gm_s, 2 * q) : __ldg(gm + 2 * q);
+          const double g1 = tab_s ? TabShared::ld(gm_s, 2 * q + 1) : __ldg(gm + 2 * q + 1);
+          alpha = fma(g0, y_get(Yc + (int64_t)(2 * q) * n_lines, own), alpha);
+          alpha = fma(g1, y_get(Yc + (int64_t)(2 * q + 1) * n_lines, own), alpha);
         }
       }
     }
-    __syncthreads();
-    const int rel = (tile + g) * W + w;
-    if (tile + g < n_tiles && rel < n_lines) {
-      const uint32_t lid = line_id[rel];
-      const bool tab_s = lid == lid_c;
-      const int64_t off = rel + (int64_t)p * M * stride;
-      double E = 0.0, alpha = 0.0;
-      const double *Yc = Yall + rel;
-      {
-        const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
-        const int q0 = max(0, pg - band), q1 = min(P_glob - 1, pg + band);
-        for (int q = q0; q <= q1; ++q) {
-          const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
-          const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
-          E = fma(g0, __ldcg(Yc + (int64_t)(2 * q) * n_lines), E);
-          E = fma(g1, __ldcg(Yc + (int64_t)(2 * q + 1) * n_lines), E);
-        }
-        if (pg > 0) {
-          const double *gm = ge - 2 * P_glob;
-          const uint32_t gm_s = ge_s - 16u * (uint32_t)P_glob;
-          const int a0 = max(0, pg - 1 - band), a1 = min(P_glob - 1, pg - 1 + band);
-          for (int q = a0; q <= a1; ++q) {
-            const double g0 = tab_s ? TabShared::ld(gm_s, 2 * q) : __ldg(gm + 2 * q);
-            const double g1 = tab_s ? TabShared::ld(gm_s, 2 * q + 1) : __ldg(gm + 2 * q + 1);
-            alpha = fma(g0, __ldcg(Yc + (int64_t)(2 * q) * n_lines), alpha);
-            alpha = fma(g1, __ldcg(Yc + (int64_t)(2 * q + 1) * n_lines), alpha);
-          }
-        }
+    __syncthreads();                     // every chunk of the line has read the peers' slots
+    if (live) {
+      // empty the peers' slots this line read (chunks pg-1-band .. pg+band of the first local chunk, the new top
+      // one of the others), for the step after next
+      const int lo = p == 0 ? max(0, pg - 1 - band) : pg + band, hi = min(P_glob - 1, pg + band);
+      for (int q = lo; q <= hi; ++q) {
+        if (q >= chunk0 && q < chunk0 + P_loc) continue;
+        reinterpret_cast<unsigned long long *>(Yc)[(int64_t)(2 * q) * n_lines] = HS2_Y_EMPTY;
+        reinterpret_cast<unsigned long long *>(Yc)[(int64_t)(2 * q + 1) * n_lines] = HS2_Y_EMPTY;
       }
-      if (tab_s) {
+      const int64_t off = rel + (int64_t)p * M * stride;
+      if (lid == lid_c) {
         chunk_bwd<M, true>(v, ts, M, alpha, E);
       } else {
         TabGlobal tg;
@@ -756,7 +768,7 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
 
 template <int M, int W>
 int launch_zfused_w(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers,
-                    const ZFlags &fl, unsigned long long step, double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
+                    double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const hs2_axis_tables &ax = d.axis[2];
   const int P_loc = (int)(d.nz / M);
@@ -777,20 +789,20 @@ int launch_zfused_w(hs2_plan *pl, double *data, const double *Tin, double *Tout,
   if (blocks > (n_tiles + G - 1) / G) blocks = (n_tiles + G - 1) / G;
   dim3 block(W, P_loc, G);
   kern<<<blocks, block, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Yall, ax.pitch, row0, nz_loc, d.z_chunks_global,
-                                    d.z_chunk0, ax.band, d.ny * d.nx, n_lines, n_tiles, peers, fl, step,
-                                    (long long)(timeout_s * 1.9e9), status);
+                                    d.z_chunk0, ax.band, d.ny * d.nx, n_lines, n_tiles, peers, (long long)(timeout_s * 1.9e9),
+                                    status);
   HS2_CUDA_CHECK(cudaGetLastError());
   pl->last_kernel[2] = HS2_K_Z_SLAB;
   return HS2_OK;
 }
 
 template <int M>
-int launch_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers, const ZFlags &fl,
-                  unsigned long long step, double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
+int launch_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers, double timeout_s,
+                  int *status, int *tile_lines, cudaStream_t st) {
   const int P_loc = (int)(pl->d.nz / M);
   HS2_REQUIRE(P_loc * 8 <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
-  if (P_loc * 16 <= 256) return launch_zfused_w<M, 16>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
-  return launch_zfused_w<M, 8>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+  if (P_loc * 16 <= 256) return launch_zfused_w<M, 16>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+  return launch_zfused_w<M, 8>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
 }
 
 template <int M, int W>
@@ -857,10 +869,9 @@ int hs2_zdist(hs2_plan *pl, int phase, double *data, const double *Tin, double *
   }
 }
 
-// fused slab z sweep; tile_lines != NULL: only report the lines per tile (one flag per tile in the mailboxes)
+// fused slab z sweep; tile_lines != NULL: only report the lines per tile
 int hs2_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, int n_peers, const uint64_t *peer_y,
-               const uint64_t *wait_flags, const uint64_t *sig_flags, uint64_t step, double timeout_s, int *status,
-               int *tile_lines, cudaStream_t st) {
+               double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
   const hs2_plan_desc &d = pl->d;
   const int M = d.axis[2].chunk;
   HS2_REQUIRE(d.z_chunks_global > 0, "plan is not part of a z-slab decomposition");
@@ -868,23 +879,25 @@ int hs2_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, doub
               "distributed z sweep needs chunk tables and nz (%lld) divisible by the chunk size (%d)", (long long)d.nz, M);
   HS2_REQUIRE(d.ny * d.nx < ((int64_t)1 << 31), "grid too large");
   ZPeers peers;
-  ZFlags fl;
-  peers.n = fl.n = 0;
+  peers.n = 0;
   if (!tile_lines) {
-    HS2_REQUIRE(n_peers >= 0 && n_peers <= HS2_MAX_Z_PEERS && (n_peers == 0 || (peer_y && wait_flags && sig_flags)) && status,
-                "fused z sweep: %d peers (max %d)", n_peers, HS2_MAX_Z_PEERS);
-    peers.n = fl.n = n_peers;
-    for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
-      peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;
-      fl.wait[q] = q < n_peers ? reinterpret_cast<unsigned long long *>(wait_flags[q]) : nullptr;
-      fl.sig[q] = q < n_peers ? reinterpret_cast<unsigned long long *>(sig_flags[q]) : nullptr;
-    }
+    HS2_REQUIRE(n_peers >= 0 && n_peers <= HS2_MAX_Z_PEERS && (n_peers == 0 || peer_y) && status, "fused z sweep: %d peers (max %d)",
+                n_peers, HS2_MAX_Z_PEERS);
+    peers.n = n_peers;
+    for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) peers.y[q] = q < n_peers ? reinterpret_cast<double *>(peer_y[q]) : nullptr;
   }
   switch (M) {
-    case 8: return launch_zfused<8>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
-    case 16: return launch_zfused<16>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
-    default: return launch_zfused<32>(pl, data, Tin, Tout, Yall, peers, fl, step, timeout_s, status, tile_lines, st);
+    case 8: return launch_zfused<8>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+    case 16: return launch_zfused<16>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+    default: return launch_zfused<32>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
   }
+}
+
+int hs2_fill_empty(void *d_ptr, int64_t n_doubles, cudaStream_t st) {
+  if (n_doubles <= 0) return HS2_OK;
+  fill_u64_kernel<<<256, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(d_ptr), n_doubles, HS2_Y_EMPTY);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  return HS2_OK;
 }
 
 bool hs2_tile_supported(const hs2_plan *p, int axis) {

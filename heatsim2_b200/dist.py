@@ -64,7 +64,7 @@ class PeerExchange(object):
     HEADER = 4096
     OFF_FLAG_H_LO, OFF_FLAG_H_HI, OFF_STATUS = 2048, 2056, 3072
 
-    def __init__(self, rank, world, hops, p_loc, ny, nx, group, device, n_tiles=0):
+    def __init__(self, rank, world, hops, p_loc, ny, nx, group, device, fill_empty=False):
         self.rank, self.world, self.hops = rank, world, hops
         self.lib = _cabi.lib()
         self.peers = [r for d in range(1, hops + 1) for r in (rank - d, rank + d) if 0 <= r < world]
@@ -77,10 +77,7 @@ class PeerExchange(object):
         self.off_halo_lo = self.HEADER
         self.off_halo_hi = self.HEADER + self.plane_bytes
         self.off_y = [self.HEADER + 2 * self.plane_bytes + par * self.y_bytes for par in (0, 1)]
-        # per-tile flags of the fused z sweep: slot i holds the flags written by slab rank-hops+i (8 bytes per tile)
-        self.n_tiles = int(n_tiles)
-        self.off_tflag = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
-        total = self.off_tflag + (2 * hops + 1) * self.n_tiles * 8
+        total = self.HEADER + 2 * self.plane_bytes + 2 * self.y_bytes
         # every step below is collective: a failure on any rank (no IPC support, no
         # peer access) makes ALL ranks give up, so that they fall back to NCCL together
         ptr = ctypes.c_void_p()
@@ -91,6 +88,11 @@ class PeerExchange(object):
         if ok:
             self._own = ptr.value
             self.base[rank] = ptr.value
+            if fill_empty:
+                # fused z sweep: an interface slot is "empty" until its value arrives (the data is its own flag)
+                with torch.cuda.device(device):
+                    _cabi.check(self.lib.hs2_peer_fill_empty(ptr.value + self.off_y[0], 2 * self.y_bytes // 8, None))
+                    torch.cuda.synchronize()
         infos = [None] * world
         dist.all_gather_object(infos, (ok, handle.raw), group=group)
         ok = all(i[0] for i in infos)
@@ -119,10 +121,6 @@ class PeerExchange(object):
     def y_rows_of(self, r, parity, src):
         """where slab ``src``'s rows live in rank r's mailbox"""
         return self.y_virtual(r, parity) + src * self.slab_bytes
-
-    def tile_flags_of(self, r, src):
-        """where slab ``src``'s per-tile flags live in rank r's mailbox"""
-        return self.base[r] + self.off_tflag + (src - (r - self.hops)) * self.n_tiles * 8
 
     def status(self):
         out = torch.zeros(1, dtype=torch.int32)
@@ -235,13 +233,8 @@ class DistPlan(object):
         if self._px is None and self.use_p2p and T_in.is_cuda and self.world > 1:
             try:
                 ny, nx = self.shape[1:]
-                n_tiles = 0
-                if self.z_fused:
-                    tl = int(_cabi.lib().hs2_sweep_z_fused_tile_lines(self.plan._handle))
-                    if tl <= 0:
-                        raise NotImplementedError("fused z sweep unavailable for this slab")
-                    n_tiles = -(-(ny * nx) // tl)
-                self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device, n_tiles)
+                self._px = PeerExchange(self.rank, self.world, self.hops, self.p_loc, ny, nx, self.group, T_in.device,
+                                        fill_empty=self.z_fused)
             except NotImplementedError as exc:
                 self.use_p2p = False
                 self.p2p_unavailable = str(exc)
@@ -292,11 +285,8 @@ class DistPlan(object):
         n_lines = self.shape[1] * self.shape[2]
         if self.z_fused:
             y_arr, cnt = _u64_list([px.y_rows_of(r, par, me) for r in px.peers])
-            w_arr, _ = _u64_list([px.tile_flags_of(me, r) for r in px.peers])
-            s_arr, _ = _u64_list([px.tile_flags_of(r, me) for r in px.peers])
             _cabi.check(lib.hs2_sweep_z_fused(self.plan._handle, T_in.data_ptr(), T_out.data_ptr(), work.data_ptr(),
-                                              px.y_virtual(me, par), cnt, y_arr, w_arr, s_arr, n, self.p2p_timeout,
-                                              own + px.OFF_STATUS, st))
+                                              px.y_virtual(me, par), cnt, y_arr, self.p2p_timeout, own + px.OFF_STATUS, st))
             if ev:
                 ev[4].record(); ev[5].record(); ev[6].record()
             return T_out

@@ -322,16 +322,16 @@ int hs2_sweep_z_forward_push_cols(hs2_plan *plan, double *d_work, double *d_Y, i
 int hs2_sweep_z_backward_cols(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work,
                               const double *d_Yall, int64_t line0, int64_t n_lines, void *stream);
 /* Both halves AND the exchange in one persistent kernel: a block eliminates a tile of lines, stores its interface
- * rows into d_Yall (own rows) and the peers' mailboxes, publishes "tile t of step `step`" to every peer
- * (signal_flags[i]: this slab's flag array inside peer i's mailbox), eliminates the next tile while the peers'
- * rows travel, waits (bounded, *d_status = 1 on expiry) for wait_flags[i][t] >= step (arrays in this GPU's own
- * mailbox, written by peer i) and back-substitutes from registers: the increment is read once (24 B per cell
- * instead of 32) and no wait sits between two launches.  One flag per tile of hs2_sweep_z_fused_tile_lines(plan)
- * lines; step values must increase from call to call; d_Yall as for hs2_sweep_z_backward_cols.               */
+ * rows into d_Yall (own rows) and the peers' mailboxes (peer_Y as for hs2_sweep_z_forward_push), eliminates the next
+ * tile while the rows travel, then back-substitutes the first one from registers: the increment is read once
+ * (24 B per cell instead of 32) and no wait sits between two launches.  The interface rows are their own flags:
+ * every slot a peer writes holds an "empty" NaN pattern (hs2_peer_fill_empty, once, after hs2_peer_alloc) until the
+ * value arrives, the kernel spins (bounded, *d_status = 1 on expiry) on the slots it needs and empties them again
+ * after use.  d_Yall as for hs2_sweep_z_backward_cols; hs2_sweep_z_fused_tile_lines: lines per tile (information). */
 int hs2_sweep_z_fused(hs2_plan *plan, const double *d_T_in, double *d_T_out, double *d_work, double *d_Yall,
-                      int n_peers, const uint64_t *peer_Y, const uint64_t *wait_flags, const uint64_t *signal_flags,
-                      uint64_t step, double timeout_s, int *d_status, void *stream);
+                      int n_peers, const uint64_t *peer_Y, double timeout_s, int *d_status, void *stream);
 int hs2_sweep_z_fused_tile_lines(hs2_plan *plan);
+int hs2_peer_fill_empty(void *d_ptr, int64_t n_doubles, void *stream);
 int hs2_flag_signal(const uint64_t *flag_ptrs, int n, uint64_t value, void *stream);
 int hs2_flag_wait(const uint64_t *flag_ptrs, int n, uint64_t value,
                   double timeout_s, int *d_status, void *stream);
