@@ -331,11 +331,18 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   const int tiles_per_group = (lines_per_group + W - 1) / W;
   const int64_t n_tiles = (int64_t)n_groups * tiles_per_group;
   if (n_tiles >= ((int64_t)1 << 31)) return HS2_OK;
-  int grid = pl->sm_count * 2;
+  // resident blocks per SM: 16 warps in all (128 registers per thread), i.e. two 256-thread blocks, four of 128
+  // threads (lines of 256 rows in chunks of 32) ... as far as the tiles fit shared memory
+  static const int bps_env = getenv("HS2_STRIDED_BPS") ? atoi(getenv("HS2_STRIDED_BPS")) : 0;
+  int bps = big ? 1 : 512 / (P * W);
+  if (bps > 4) bps = 4;
+  if (bps_env > 0 && !big) bps = bps_env;
+  while (bps > 1 && (size_t)bps * (smem + 1024) > 226u * 1024) --bps;
+  int grid = pl->sm_count * bps;
   if (grid > n_tiles) grid = (int)n_tiles;
   dim3 block(W, P);
   static const int carveout_env = getenv("HS2_CARVEOUT") ? atoi(getenv("HS2_CARVEOUT")) : -1;
-  const int carveout = carveout_env >= 0 ? carveout_env : (int)(((big ? 1 : 2) * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  const int carveout = carveout_env >= 0 ? carveout_env : (int)((bps * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (use_tma) {
@@ -680,6 +687,19 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
     return x;
   };
 
+  // The phases of a tile (rows of d, forward, interface values, backward, rows of T_in, stores) follow each other
+  // inside a block and only two blocks share an SM, so every row is asked for one tile ahead: one L2 prefetch per
+  // 128-byte piece (the W lines of a row), issued by one thread per chunk
+  auto warm = [&](const double *base, int t0) {
+    const int rel0 = (t0 + g) * W;
+    if (w == 0 && t0 + g < n_tiles && rel0 < n_lines) {
+      const double *ptr = base + rel0 + (int64_t)p * M * stride;
+#pragma unroll
+      for (int t = 0; t < M; ++t) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + (int64_t)t * stride));
+    }
+  };
+  warm(Tin, tile);
+  warm(data, tile + gridDim.x * G);
   forward(tile);
 #pragma unroll
   for (int t = 0; t < M; ++t) park[t * 256] = v[t];
@@ -687,6 +707,8 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
     const int next = tile + gridDim.x * G;
     const bool has_next = next < n_tiles;
     if (has_next) {
+      warm(Tin, next);
+      warm(data, next + gridDim.x * G);
       forward(next);
 #pragma unroll
       for (int t = 0; t < M; ++t) {      // swap: the parked tile comes back, the new one is parked (own slots only)
