@@ -631,6 +631,13 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
   }
   __syncthreads();
   const int pg = chunk0 + p;
+  // the threads of line group g (W lines x all local chunks: whole warps) only ever wait for each other
+  auto group_sync = [&]() {
+    if (G == 1)
+      __syncthreads();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(W * P_loc) : "memory");
+  };
   TabShared ts;
   ts.a = smem_u32(s_tab + p * M);
   ts.pitch_b = (uint32_t)nz_loc * 8u;
@@ -720,7 +727,7 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
 #pragma unroll
       for (int t = 0; t < M; ++t) v[t] = park[t * 256];
     }
-    __syncthreads();                     // the block's own rows of `tile` are there
+    group_sync();                        // the own rows of the group's lines are there (all chunks of a line sit in one group)
     const int rel = (tile + g) * W + w;
     const bool live = tile + g < n_tiles && rel < n_lines;
     uint32_t lid = 0;
@@ -751,7 +758,7 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
         }
       }
     }
-    __syncthreads();                     // every chunk of the line has read the peers' slots
+    group_sync();                        // every chunk of the line has read the peers' slots
     if (live) {
       // empty the peers' slots this line read (chunks pg-1-band .. pg+band of the first local chunk, the new top
       // one of the others), for the step after next

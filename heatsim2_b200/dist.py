@@ -164,7 +164,7 @@ class DistPlan(object):
         self.p2p_ranges = int(os.environ.get("HS2_DIST_P2P_RANGES", "2"))       # line ranges of the peer-memory z sweep (1 or 2)
         # one persistent kernel for the whole z sweep (forward, exchange through the mailboxes, backward);
         # HS2_DIST_Z_FUSED=0: forward / flag / backward launches per line range
-        self.z_fused = os.environ.get("HS2_DIST_Z_FUSED", "1") != "0"
+        self.z_fused = os.environ.get("HS2_DIST_Z_FUSED", "0") != "0"
         self._bufs = {}
         self.use_p2p = os.environ.get("HS2_DIST_P2P", "1") != "0"
         # upper bound of a flag wait.  Ranks of one job drift apart by far more than a

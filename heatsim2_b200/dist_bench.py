@@ -56,6 +56,8 @@ def run(args, shape, workload_name, clock_sampler=None):
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     _cabi.lib()
+    if getattr(args, "shape", ""):
+        shape = tuple(int(v) for v in args.shape.split(","))      # global grid override (experiments)
     t_p = time.perf_counter()
     prob = problems.uniform_slab(hs, shape=shape, random_T0=False)      # the caller's arrays (reference API): numpy, global grid
     problem_s = time.perf_counter() - t_p

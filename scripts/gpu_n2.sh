@@ -5,8 +5,8 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 if [ "${3:-no}" = "tests" ]; then timeout 900 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -6; fi
-for FUSED in 1 0; do
-HS2_DIST_Z_FUSED=$FUSED timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 3 --scaling $SC 2>gpurun_out/dist${N}_${SC}_f$FUSED.err | tail -1 > gpurun_out/dist${N}_${SC}_f$FUSED.json
+for FUSED in ${FUSED_LIST:-1 0}; do
+HS2_DIST_Z_FUSED=$FUSED timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 3 --scaling $SC $EXTRA 2>gpurun_out/dist${N}_${SC}_f$FUSED.err | tail -1 > gpurun_out/dist${N}_${SC}_f$FUSED.json
 python - <<PY
 import json
 try:
