@@ -372,7 +372,8 @@ def run_b200_single(args):
     e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
            "ms_per_step": e2e_ms, "steps": e2e_steps,
            "api": "heatsim2_b200.run_adi_steps(numpy float64 array in -> new numpy array out), the reference's call; "
-                  "pageable user arrays are staged through pinned buffers in pipelined chunks"}
+                  "the returned arrays live in page-locked memory (caching host allocator), so after the first step "
+                  "(pageable input, staged through pinned chunks) both copies of a step are single DMAs"}
     # the same round trip with caller-pinned host tensors (no staging copies): what PCIe alone costs
     H_in = T_host
     H_out = torch.empty(shape, dtype=torch.float64).pin_memory()

@@ -304,10 +304,9 @@ def compile_problem(z0, y0, x0,
             raise ValueError("top_surface_*_curvatures must have shape (ny, nx) = %r" % ((ny, nx),))
         curv_pairs, curv_id = np.unique(np.stack([cy.reshape(-1), cx.reshape(-1)], axis=1), axis=0, return_inverse=True)
         curv_id = curv_id.reshape(ny, nx)
-        if len(curv_pairs) * nz > 65536:
-            raise NotImplementedError(
-                "curved-surface mode with %d distinct curvature pairs x %d layers needs per-cell coefficients; "
-                "the class tables hold 65536 equation classes" % (len(curv_pairs), nz))
+        # (more than 65536 (pair, layer) combinations - a curvature MAP on a large grid - still work: 4-byte class
+        # ids and the whole-line kernels, plan.py wide_ids; the symbolic pipeline then runs once per class, which is
+        # what the reference does per cell)
         extra_radix = len(curv_pairs) * nz
         extra = torch.from_numpy(curv_id[None, :, :] * nz + np.arange(nz)[:, None, None]).to(torch.int64)
         kk = np.arange(nz, dtype=np.float64)[:, None, None]

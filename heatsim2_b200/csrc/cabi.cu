@@ -39,9 +39,11 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
   *out = nullptr;
   HS2_REQUIRE(desc->nz > 0 && desc->ny > 0 && desc->nx > 0, "hs2_plan_create: empty grid %lld x %lld x %lld",
               (long long)desc->nz, (long long)desc->ny, (long long)desc->nx);
-  HS2_REQUIRE(desc->class_id_bytes == 1 || desc->class_id_bytes == 2, "hs2_plan_create: class_id_bytes must be 1 or 2");
-  HS2_REQUIRE(desc->n_classes > 0 && desc->n_classes <= (desc->class_id_bytes == 1 ? 256 : 65536),
+  HS2_REQUIRE(desc->class_id_bytes == 1 || desc->class_id_bytes == 2 || desc->class_id_bytes == 4,
+              "hs2_plan_create: class_id_bytes must be 1, 2 or 4");
+  HS2_REQUIRE(desc->n_classes > 0 && (desc->class_id_bytes == 4 || desc->n_classes <= (desc->class_id_bytes == 1 ? 256 : 65536)),
               "hs2_plan_create: n_classes %d out of range for %d-byte ids", desc->n_classes, desc->class_id_bytes);
+  HS2_REQUIRE(desc->class_id_bytes != 4 || desc->z_chunks_global == 0, "hs2_plan_create: 4-byte class ids are not supported in z-slab plans");
   HS2_REQUIRE(desc->d_class_id && desc->d_class_coef, "hs2_plan_create: NULL class tables");
   for (int a = 0; a < 3; ++a)
     HS2_REQUIRE(desc->axis[a].d_line_id && desc->axis[a].d_lu && desc->axis[a].n_unique > 0,
@@ -60,6 +62,9 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
     return HS2_E_NOMEM;
   }
   p->d = *desc;
+  // 4-byte class ids (per-cell equations, e.g. a curvature map: up to 2^31 classes): the coefficient rows do not fit
+  // shared memory and every line is its own class - the whole-line global-memory kernels run all three sweeps
+  if (desc->class_id_bytes == 4) p->d.flags |= HS2_FLAG_FORCE_FALLBACK;
   p->owned = nullptr;
   p->n = desc->nz * desc->ny * desc->nx;
   p->sm_count = prop.multiProcessorCount;

@@ -632,8 +632,10 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
   __syncthreads();
   const int pg = chunk0 + p;
   // the threads of line group g (W lines x all local chunks: whole warps) only ever wait for each other
+  // (named barriers: whole warps only, ids 1..15)
+  const bool own_bar = G > 1 && G <= 15 && ((W * P_loc) & 31) == 0;
   auto group_sync = [&]() {
-    if (G == 1)
+    if (!own_bar)
       __syncthreads();
     else
       asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(W * P_loc) : "memory");
@@ -795,6 +797,165 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
   }
 }
 
+// Warp-autonomous variant of the fused slab z sweep, for thin slabs: ALL chunks of a line sit in one warp
+// (WL = 32 / P_loc lines x P_loc chunks, lane = p * WL + w; WL lines = WL * 8 contiguous bytes per row), so the
+// interface values of the own chunks travel by shuffle, the peers' values are polled from the mailbox slots
+// (self-validating, see z_fused), and there is no barrier at all: sixteen independent warps per SM, each in its own
+// phase.  No parking either: while a warp waits for its peers' rows the other warps use the memory system.
+template <int M, int WL>
+__global__ void __launch_bounds__(256, 2)
+z_fused_warp(const double *__restrict__ data, const double *__restrict__ Tin, double *__restrict__ Tout,
+             const uint32_t *__restrict__ line_id, const double *__restrict__ tab, const double *__restrict__ GE,
+             double *Yall, int pitch, int row0, int nz_loc, int P_glob, int chunk0, int band, int64_t stride, int n_lines,
+             int n_tiles, ZPeers peers, long long max_cycles, int *status) {
+  constexpr int P_loc = 32 / WL;
+  extern __shared__ __align__(16) double zsm[];
+  double *s_tab = zsm;                                   // [HS2_T_PLANES][nz_loc]
+  double *s_ge = s_tab + HS2_T_PLANES * nz_loc;          // [P_loc + 1][2 P_glob]: rows chunk0-1 .. chunk0+P_loc-1
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int w = lane % WL, p = lane / WL;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int tile = (blockIdx.x * blockDim.x + tid) >> 5;
+  const uint32_t lid_c = line_id[min((int64_t)((blockIdx.x * blockDim.x) >> 5) * WL, (int64_t)n_lines - 1)];
+  for (int e = tid; e < HS2_T_PLANES * nz_loc; e += blockDim.x)
+    s_tab[e] = tab[((int64_t)lid_c * HS2_T_PLANES + e / nz_loc) * pitch + row0 + e % nz_loc];
+  for (int e = tid; e < (P_loc + 1) * 2 * P_glob; e += blockDim.x) {
+    const int row = chunk0 - 1 + e / (2 * P_glob);
+    s_ge[e] = row >= 0 ? GE[((int64_t)lid_c * P_glob + row) * (2 * P_glob) + e % (2 * P_glob)] : 0.0;
+  }
+  __syncthreads();
+  const int pg = chunk0 + p;
+  TabShared ts;
+  ts.a = smem_u32(s_tab + p * M);
+  ts.pitch_b = (uint32_t)nz_loc * 8u;
+  const uint32_t ge_s = smem_u32(s_ge + (p + 1) * 2 * P_glob);      // row pg; row pg-1 sits just before it
+  bool dead = *reinterpret_cast<volatile int *>(status) != 0;
+  const long long t_begin = clock64();
+
+  for (; tile < n_tiles; tile += warps) {
+    const int rel = tile * WL + w;
+    const bool live = rel < n_lines;
+    const int relc = live ? rel : n_lines - 1;           // (lanes without a line go through the motions on the last one)
+    const uint32_t lid = line_id[relc];
+    const bool tab_s = lid == lid_c;
+    const int64_t off = relc + (int64_t)p * M * stride;
+    double v[M];
+#pragma unroll
+    for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
+    double yf, last;
+    TabGlobal tg;
+    tg.b = tab + ((int64_t)lid * HS2_T_PLANES) * pitch + row0 + p * M;
+    tg.pitch = pitch;
+    if (tab_s)
+      yf = chunk_fwd<M, true>(v, ts, M, &last);
+    else
+      yf = chunk_fwd<M, true>(v, tg, M, &last);
+    if (live) {
+      const int64_t y0 = (int64_t)(2 * p) * n_lines + rel, y1 = y0 + n_lines;
+#pragma unroll
+      for (int q = 0; q < HS2_MAX_Z_PEERS; ++q) {
+        if (q < peers.n) {
+          peers.y[q][y0] = yf;
+          peers.y[q][y1] = last;
+        }
+      }
+    }
+    // interface values of the chunks pg-1-band .. pg+band: own chunks by shuffle, the peers' from their slots
+    double E = 0.0, alpha = 0.0;
+    double *Yc = Yall + relc;
+    const double *ge = GE + ((int64_t)lid * P_glob + pg) * (2 * P_glob);
+    for (int d = -band - 1; d <= band; ++d) {
+      const int q = pg + d;
+      const int src = lane + d * WL;
+      const double ys = __shfl_sync(0xffffffffu, yf, src & 31), ls = __shfl_sync(0xffffffffu, last, src & 31);
+      if (q < 0 || q >= P_glob) continue;
+      double y_f = ys, y_l = ls;
+      const bool own = q >= chunk0 && q < chunk0 + P_loc;
+      if (!own) {
+        const double *s0 = Yc + (int64_t)(2 * q) * n_lines, *s1 = s0 + n_lines;
+        y_f = __ldcg(s0), y_l = __ldcg(s1);
+        if (live && !dead) {
+          while (__double_as_longlong(y_f) == (long long)HS2_Y_EMPTY || __double_as_longlong(y_l) == (long long)HS2_Y_EMPTY) {
+            if (clock64() - t_begin > max_cycles) {
+              atomicExch(status, 1);
+              dead = true;
+              break;
+            }
+            __nanosleep(64);
+            y_f = __ldcg(s0), y_l = __ldcg(s1);
+          }
+        }
+      }
+      if (d >= -band) {      // row pg: chunks pg-band .. pg+band
+        const double g0 = tab_s ? TabShared::ld(ge_s, 2 * q) : __ldg(ge + 2 * q);
+        const double g1 = tab_s ? TabShared::ld(ge_s, 2 * q + 1) : __ldg(ge + 2 * q + 1);
+        E = fma(g0, y_f, E);
+        E = fma(g1, y_l, E);
+      }
+      if (pg > 0 && d < band) {      // row pg-1: chunks pg-1-band .. pg-1+band
+        const double g0 = tab_s ? TabShared::ld(ge_s - 16u * (uint32_t)P_glob, 2 * q) : __ldg(ge - 2 * P_glob + 2 * q);
+        const double g1 = tab_s ? TabShared::ld(ge_s - 16u * (uint32_t)P_glob, 2 * q + 1) : __ldg(ge - 2 * P_glob + 2 * q + 1);
+        alpha = fma(g0, y_f, alpha);
+        alpha = fma(g1, y_l, alpha);
+      }
+    }
+    __syncwarp();                        // every chunk of the line has read the peers' slots
+    if (live) {
+      const int lo = p == 0 ? max(0, pg - 1 - band) : pg + band, hi = min(P_glob - 1, pg + band);
+      for (int q = lo; q <= hi; ++q) {
+        if (q >= chunk0 && q < chunk0 + P_loc) continue;
+        reinterpret_cast<unsigned long long *>(Yc)[(int64_t)(2 * q) * n_lines] = HS2_Y_EMPTY;
+        reinterpret_cast<unsigned long long *>(Yc)[(int64_t)(2 * q + 1) * n_lines] = HS2_Y_EMPTY;
+      }
+    }
+    if (tab_s)
+      chunk_bwd<M, true>(v, ts, M, alpha, E);
+    else
+      chunk_bwd<M, true>(v, tg, M, alpha, E);
+    if (live) {
+      double tin[2][8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tin[0][q] = Tin[off + (int64_t)q * stride];
+#pragma unroll
+      for (int gb = 0; gb < M; gb += 8) {
+        if (gb + 8 < M) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tin[((gb >> 3) + 1) & 1][q] = Tin[off + (int64_t)(gb + 8 + q) * stride];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[(gb >> 3) & 1][q] + v[gb + q];
+      }
+    }
+  }
+}
+
+template <int M, int WL>
+int launch_zfused_warp(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers,
+                       double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
+  const hs2_plan_desc &d = pl->d;
+  const hs2_axis_tables &ax = d.axis[2];
+  constexpr int P_loc = 32 / WL;
+  if (tile_lines) {
+    *tile_lines = WL;
+    return HS2_OK;
+  }
+  const int n_lines = (int)(d.ny * d.nx);
+  const int n_tiles = (n_lines + WL - 1) / WL;
+  const int row0 = d.z_chunk0 * M;
+  const int nz_loc = (int)d.nz;
+  const size_t smem = ((size_t)HS2_T_PLANES * nz_loc + (size_t)(P_loc + 1) * 2 * d.z_chunks_global) * sizeof(double);
+  HS2_REQUIRE(smem <= 100 * 1024, "fused z sweep: tables need %zu B of shared memory", smem);
+  auto kern = z_fused_warp<M, WL>;
+  if (smem > 48 * 1024) HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = pl->sm_count * 2;
+  if (blocks > (n_tiles + 7) / 8) blocks = (n_tiles + 7) / 8;
+  kern<<<blocks, 256, smem, st>>>(data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, Yall, ax.pitch, row0, nz_loc, d.z_chunks_global,
+                                  d.z_chunk0, ax.band, d.ny * d.nx, n_lines, n_tiles, peers, (long long)(timeout_s * 1.9e9), status);
+  HS2_CUDA_CHECK(cudaGetLastError());
+  pl->last_kernel[2] = HS2_K_Z_SLAB;
+  return HS2_OK;
+}
+
 template <int M, int W>
 int launch_zfused_w(hs2_plan *pl, double *data, const double *Tin, double *Tout, double *Yall, const ZPeers &peers,
                     double timeout_s, int *status, int *tile_lines, cudaStream_t st) {
@@ -830,6 +991,13 @@ int launch_zfused(hs2_plan *pl, double *data, const double *Tin, double *Tout, d
                   int *status, int *tile_lines, cudaStream_t st) {
   const int P_loc = (int)(pl->d.nz / M);
   HS2_REQUIRE(P_loc * 8 <= 256, "distributed z sweep: %d local chunks of %d rows do not fit a block", P_loc, M);
+  // thin slabs: all chunks of a line in one warp (8 lines x 4 chunks, 16 x 2, 32 x 1), no barriers
+  static const bool no_warp = getenv("HS2_ZFUSED_BLOCK") != nullptr && getenv("HS2_ZFUSED_BLOCK")[0] == '1';
+  if (!no_warp && pl->d.nz % M == 0) {
+    if (P_loc == 4) return launch_zfused_warp<M, 8>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+    if (P_loc == 2) return launch_zfused_warp<M, 16>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+    if (P_loc == 1) return launch_zfused_warp<M, 32>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
+  }
   if (P_loc * 16 <= 256) return launch_zfused_w<M, 16>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
   return launch_zfused_w<M, 8>(pl, data, Tin, Tout, Yall, peers, timeout_s, status, tile_lines, st);
 }

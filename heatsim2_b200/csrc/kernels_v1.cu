@@ -121,6 +121,9 @@ int hs2_v1_sweep_x(hs2_plan *p, const double *T, double *W, const hs2_source *sr
   if (d.class_id_bytes == 1)
     rhs_kernel<uint8_t><<<blocks, threads, 0, st>>>(T, W, (const uint8_t *)d.d_class_id, d.d_class_coef, vol, tab,
                                                     dense, halo_lo, halo_hi, d.nz, d.ny, d.nx);
+  else if (d.class_id_bytes == 4)
+    rhs_kernel<uint32_t><<<blocks, threads, 0, st>>>(T, W, (const uint32_t *)d.d_class_id, d.d_class_coef, vol, tab,
+                                                     dense, halo_lo, halo_hi, d.nz, d.ny, d.nx);
   else
     rhs_kernel<uint16_t><<<blocks, threads, 0, st>>>(T, W, (const uint16_t *)d.d_class_id, d.d_class_coef, vol, tab,
                                                      dense, halo_lo, halo_hi, d.nz, d.ny, d.nx);

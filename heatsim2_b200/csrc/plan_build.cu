@@ -597,6 +597,7 @@ static int bt_build(const hs2_build_desc *b, hs2_owned *own, hs2_plan_desc *d) {
                              b->n_classes, a, own->h_line_id[axis], weight);
     if (rc) return rc;
     int M = b->chunk[axis];
+    if (sizeof(CID) == 4) M = -1;      // per-cell classes: whole-line kernels, Thomas factors only
     if (M == 0) M = glob ? 0 : bt_choose_chunk(L, axis, 32, x_tma, x_warp);
     if (M < 0) M = 0;
     HS2_REQUIRE(M == 0 || M == 8 || M == 16 || M == 32, "hs2_plan_build: chunk[%d] = %d (0, 8, 16 or 32)", axis, M);
@@ -634,9 +635,10 @@ int hs2_plan_build(const hs2_build_desc *b, hs2_plan **out) {
   HS2_REQUIRE(b && out, "hs2_plan_build: NULL argument");
   *out = nullptr;
   HS2_REQUIRE(b->nz > 0 && b->ny > 0 && b->nx > 0, "hs2_plan_build: empty grid");
-  HS2_REQUIRE(b->class_id_bytes == 1 || b->class_id_bytes == 2, "hs2_plan_build: class_id_bytes must be 1 or 2");
-  HS2_REQUIRE(b->n_classes > 0 && b->n_classes <= (b->class_id_bytes == 1 ? 256 : 65536), "hs2_plan_build: n_classes %d out of range",
-              b->n_classes);
+  HS2_REQUIRE(b->class_id_bytes == 1 || b->class_id_bytes == 2 || b->class_id_bytes == 4, "hs2_plan_build: class_id_bytes must be 1, 2 or 4");
+  HS2_REQUIRE(b->n_classes > 0 && (b->class_id_bytes == 4 || b->n_classes <= (b->class_id_bytes == 1 ? 256 : 65536)),
+              "hs2_plan_build: n_classes %d out of range", b->n_classes);
+  HS2_REQUIRE(b->class_id_bytes != 4 || !b->d_class_id_global, "hs2_plan_build: 4-byte class ids are not supported in z-slab plans");
   HS2_REQUIRE(b->d_class_id && b->h_class_coef, "hs2_plan_build: NULL class tables");
   HS2_REQUIRE(b->nx < ((int64_t)1 << 30) && b->ny < ((int64_t)1 << 30) && b->nz < ((int64_t)1 << 30), "hs2_plan_build: grid too large");
   if (b->d_class_id_global)
@@ -652,7 +654,8 @@ int hs2_plan_build(const hs2_build_desc *b, hs2_plan **out) {
   }
   hs2_plan_desc d;
   memset(&d, 0, sizeof(d));
-  int rc = b->class_id_bytes == 1 ? bt_build<uint8_t>(b, own, &d) : bt_build<uint16_t>(b, own, &d);
+  int rc = b->class_id_bytes == 1 ? bt_build<uint8_t>(b, own, &d)
+                                  : (b->class_id_bytes == 2 ? bt_build<uint16_t>(b, own, &d) : bt_build<uint32_t>(b, own, &d));
   if (!rc) rc = hs2_plan_create(&d, out);
   cudaSetDevice(prev);
   if (rc) {

@@ -334,8 +334,13 @@ class AdiPlan(object):
         self.materials = materials
         self.class_coef = np.ascontiguousarray(class_coef, dtype=np.float64)     # [nc, 8] un-scaled
         self.n_classes = self.class_coef.shape[0]
-        if self.n_classes > 65536:
-            raise NotImplementedError("more than 65536 equation classes (%d)" % self.n_classes)
+        if self.n_classes >= (1 << 31):
+            raise NotImplementedError("more than 2^31 equation classes (%d)" % self.n_classes)
+        # more than 65536 classes (per-cell equations: a curvature MAP in curved-surface mode), or HS2_WIDE_IDS=1:
+        # 4-byte class ids, whole-line kernels (the class table does not fit shared memory, every line is unique)
+        self.wide_ids = self.n_classes > 65536 or os.environ.get("HS2_WIDE_IDS", "0") == "1"
+        if self.wide_ids and slab is not None:
+            raise NotImplementedError("z-slab plans need at most 65536 equation classes (%d)" % self.n_classes)
         self.slab = None
         if slab is None:
             self.class_id = self._pack_ids(class_id).reshape(self.shape).contiguous()
@@ -372,6 +377,8 @@ class AdiPlan(object):
 
     def _pack_ids(self, class_id):
         cid = class_id if isinstance(class_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(class_id))
+        if self.wide_ids:
+            return cid.to(torch.int32)
         want = torch.uint8 if self.n_classes <= 256 else torch.int16    # int16 carries u16 bit patterns
         if cid.dtype != want:
             cid = cid.to(torch.int64).to(want) if want == torch.uint8 else cid.to(torch.int32).to(torch.int16)
@@ -386,7 +393,7 @@ class AdiPlan(object):
                  (cid[:, 0], GYM, "y-min"), (cid[:, -1], GYP, "y-max"),
                  (cid[:, :, 0], GXM, "x-min"), (cid[:, :, -1], GXP, "x-max"))
         for sl, col, name in faces:
-            ids = torch.unique(sl.to(torch.int32) & 0xFFFF).cpu().numpy()
+            ids = torch.unique(sl.to(torch.int32) & (0xFFFF if sl.dtype == torch.int16 else 0x7FFFFFFF)).cpu().numpy()
             if np.any(self.class_coef[ids, col] != 0.0):
                 raise ValueError("Equation exceeds bounds of domain on the %s face. "
                                  "Are external boundaries set correctly?" % name)
@@ -411,6 +418,8 @@ class AdiPlan(object):
         if self._handle is not None:
             return [(i.chunk, i.n_chunks) for i in (self.axis_info(a) for a in range(3))]
         out = []
+        if self.wide_ids:
+            return [(0, 0)] * 3
         for axis in range(3):
             if axis == 2 and self.slab is not None:
                 M = slab_chunk(self.shape[0])
@@ -804,10 +813,23 @@ class AdiPlan(object):
         self.ensure_device()
         with torch.cuda.device(self._dev):
             d_T = self._buf("T")
-            self._upload(torch.from_numpy(arr), d_T)
+            h_in = torch.from_numpy(arr)
+            if h_in.is_pinned():
+                d_T.copy_(h_in, non_blocking=True)        # an array this function returned earlier: DMA straight from it
+            else:
+                self._upload(h_in, d_T)                   # the user's pageable array: staged through pinned chunks
             self.step_device(d_T, d_T, t, dt, volumetric_elements, volumetric)
-            result = torch.empty(self.shape, dtype=torch.float64)       # the new array the caller gets, like the reference
-            self._download(d_T, result)
+            # The new array the caller gets (like the reference) lives in page-locked memory (torch's caching host
+            # allocator re-uses the block of an array the caller has dropped), so the download is one DMA and, in the
+            # usual loop T = run_adi_steps(..., T, ...), so is the next step's upload.  HS2_PINNED_RESULTS=0: plain
+            # pageable arrays (staged copies both ways).
+            if os.environ.get("HS2_PINNED_RESULTS", "1") != "0":
+                result = torch.empty(self.shape, dtype=torch.float64, pin_memory=True)
+                result.copy_(d_T, non_blocking=True)
+                torch.cuda.current_stream(self._dev).synchronize()
+            else:
+                result = torch.empty(self.shape, dtype=torch.float64)
+                self._download(d_T, result)
             return result.numpy()
 
     # numpy in / numpy out (the reference's contract): the user's arrays are pageable, so they travel through two
@@ -871,7 +893,7 @@ class AdiPlan(object):
             raise MemoryError("reference_matrices is meant for small grids")
         perm = _STAGES[stepnum][1]
         nz, ny, nx = self.shape
-        cid = self.class_id.cpu().numpy().astype(np.int64) & 0xFFFF
+        cid = self.class_id.cpu().numpy().astype(np.int64) & (0xFFFF if self.class_id.dtype == torch.int16 else 0x7FFFFFFF)
         cc = self.class_coef[cid]                       # [nz,ny,nx,8]
         M = cc[..., M_]
         g = {2: (cc[..., GXM], cc[..., GXP]), 1: (cc[..., GYM], cc[..., GYP]), 0: (cc[..., GZM], cc[..., GZP])}

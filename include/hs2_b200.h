@@ -111,7 +111,7 @@ typedef struct hs2_axis_tables {
 typedef struct hs2_plan_desc {
   int64_t nz, ny, nx;          /* local grid (a z-slab in multi-GPU runs)     */
   int32_t n_classes;
-  int32_t class_id_bytes;      /* 1 (u8) or 2 (u16)                           */
+  int32_t class_id_bytes;      /* 1 (u8), 2 (u16) or 4 (u32: whole-line kernels only) */
   const void *d_class_id;      /* device, [nz][ny][nx]                        */
   const double *d_class_coef;  /* device, [n_classes][HS2_COEF_STRIDE]        */
   hs2_axis_tables axis[3];
@@ -172,7 +172,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out);
 typedef struct hs2_build_desc {
   int64_t nz, ny, nx;
   int32_t n_classes;
-  int32_t class_id_bytes;        /* 1 (u8) or 2 (u16)                           */
+  int32_t class_id_bytes;        /* 1 (u8), 2 (u16) or 4 (u32: per-cell equations, whole-line kernels) */
   const void *d_class_id;        /* device [nz][ny][nx]; must outlive the plan  */
   const double *h_class_coef;    /* host [n_classes][8]                         */
   int32_t device;

@@ -44,6 +44,7 @@ CASES = {
     "line_1d": ("uniform_slab", dict(shape=(1, 1, 40), nsteps=5), (1, 5)),
     "plane_2d": ("uniform_slab", dict(shape=(1, 24, 20), nsteps=5), (1, 5)),
     "c6_curved_plate": ("curved_plate", dict(nz=24, ny=20, nx=28, nsteps=12), (1, 3, 12)),
+    "c7_curved_map": ("curved_map", dict(nz=8, ny=10, nx=12, nsteps=6), (1, 3, 6)),     # one curvature pair per (j, i)
 }
 
 

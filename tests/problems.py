@@ -179,5 +179,17 @@ def curved_plate(hs, nz=24, ny=20, nx=28, nsteps=12, seed=21):
     return d
 
 
-ALL = {"curved_plate": curved_plate, "steelonfoam": steelonfoam, "uniform_slab": uniform_slab, "steelonwater": steelonwater,
+def curved_map(hs, nz=8, ny=10, nx=12, nsteps=6, seed=22):
+    """Curved-surface mode with a SMOOTH curvature map: every (j, i) has its own pair of curvatures (a measured
+    surface), so every cell has its own geometry and - with the depth - its own equation
+    (crank_nicolson.pyx:388-458 evaluates it per cell).  Otherwise the curved_plate recipe on a small grid."""
+    d = curved_plate(hs, nz=nz, ny=ny, nx=nx, nsteps=nsteps, seed=seed)
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    cy = (1.0 / 50e-3) * (1.0 + 0.25 * np.sin(0.7 * jj + 0.31 * ii) + 0.01 * jj)
+    cx = (1.0 / 120e-3) * np.cos(0.45 * ii - 0.2 * jj) - 0.002 * ii * jj
+    d["setup_args"] = d["setup_args"][:-2] + (cy, cx)
+    return d
+
+
+ALL = {"curved_plate": curved_plate, "curved_map": curved_map, "steelonfoam": steelonfoam, "uniform_slab": uniform_slab, "steelonwater": steelonwater,
        "composite": composite, "sources_demo": sources_demo}

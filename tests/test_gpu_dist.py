@@ -116,6 +116,9 @@ def test_two_gpus_match_one_gpu_and_oracle(name, kwargs, nsteps, p2p):
     (4, "uniform_slab", dict(shape=(128, 48, 64)), 3, False),
     (2, "sources_demo", dict(nz=16, ny=10, nx=14), 6, True),
     (2, "composite", dict(nz=64, ny=96, nx=128, ply=8), 3, True),      # 768 tiles: several per block, two line classes
+    (2, "uniform_slab", dict(shape=(256, 24, 40)), 3, True),           # 4 local chunks of 32: warp-autonomous fused kernel, 8 lines per warp
+    (2, "composite", dict(nz=128, ny=24, nx=40, ply=8), 3, True),      # 2 local chunks: 16 lines per warp, two line classes
+    (2, "uniform_slab", dict(shape=(512, 16, 24)), 3, True),           # 8 local chunks: block kernel, two line groups with their own barriers
 ])
 def test_peer_memory_transport_between_processes_on_one_gpu(world, name, kwargs, nsteps, fused):
     """The mailbox / flag / step-parity protocol of the peer-memory transport (dist.py PeerExchange, peer.cu,

@@ -162,3 +162,33 @@ def test_constant_bank_tables_are_bit_identical(hs, name, kwargs):
     from heatsim2_b200 import _cabi
     assert all(int(plan.copy_table(a, _cabi.TAB_UCODE, np.uint8).sum()) > 0 for a in range(3)), "no uniform chunks found"
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,kwargs,nsteps", [
+    ("curved_map", dict(), 6),                            # one curvature pair per (j, i): every cell its own equation
+    ("steelonwater", dict(nz=16, ny=14, nx=48), 3),
+    ("sources_demo", dict(), 6),
+    ("uniform_slab", dict(shape=(9, 20, 31)), 3),
+])
+def test_four_byte_class_ids_whole_line_kernels(hs, monkeypatch, name, kwargs, nsteps):
+    """More than 65536 equation classes (a curvature MAP on a large grid) run with 4-byte class ids on the whole-line
+    kernels (VERDICT r01 'per-cell curvature').  Forced here on small problems (HS2_WIDE_IDS=1): same fields as the
+    oracle, and for the smooth map the reference's own golden vector (tests/golden/c7_curved_map.npz)."""
+    import adi_oracle
+    monkeypatch.setenv("HS2_WIDE_IDS", "1")
+    prob = problems.ALL[name](hs, **kwargs)
+    got, plan = _run_plan(hs, prob, nsteps)
+    assert plan.wide_ids and plan.class_id.element_size() == 4
+    assert plan.last_kernels() == ("whole-line",) * 3
+    assert util.relerr(got, adi_oracle.run(prob, nsteps=nsteps)) <= 1e-12 * nsteps
+    if name == "curved_map":
+        z, meta = util.load_golden("c7_curved_map")
+        assert util.relerr(got, z["T_%d" % nsteps]) <= 1e-12 * nsteps
+
+
+def test_curvature_map_class_count(hs):
+    """the smooth map: one geometry class per (curvature pair, layer) - the two-byte ids of the tile kernels"""
+    prob = problems.curved_map(hs)
+    P, S = hs.setup(*prob["setup_args"])
+    nz, ny, nx = prob["shape"]
+    assert P.plan.n_classes >= ny * nx * (nz - 1) // 2 and not P.plan.wide_ids
