@@ -24,7 +24,10 @@ def short(name):
             how = "TMA prefetch" if args[3] in ("1", "true") else "cp.async prefetch"
             return "strided_sweep_tma (%s, persistent, %s)" % ("z" if final else "y", how)
         return "strided_sweep (%s, register loads)" % ("z" if final else "y")
-    for key, lab in (("sweep_xf_kernel", "sweep_xf_kernel (sweep_x: 5-point RHS + folded solve)"),
+    for key, lab in (("sweep_xw2_kernel", "sweep_xw2_kernel (sweep_x: warp per line pair, two lines per lane, TMA boxes)"),
+                     ("sweep_xw_kernel", "sweep_xw_kernel (sweep_x: warp per line, TMA boxes)"),
+                     ("sweep_xt_kernel", "sweep_xt_kernel (sweep_x: TMA-fed patches)"),
+                     ("sweep_xf_kernel", "sweep_xf_kernel (sweep_x: 5-point RHS + folded solve)"),
                      ("sweep_x_kernel", "sweep_x_kernel (x: RHS + solve)"),
                      ("z_forward", "z_forward (slab)"), ("z_backward", "z_backward (slab)"),
                      ("rhs_kernel", "rhs_kernel (fallback)"), ("thomas_kernel", "thomas_kernel (fallback)")):
@@ -62,12 +65,12 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM r
         ("smsp__inst_executed.sum", "warp instructions")]
 
 
-def full(path):
+def full(path, cells=512 ** 3, write_traffic=True):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     traffic = {}
-    print("# ncu --set full (--clock-control none) of the three sweep kernels, 512^3, one launch each\n")
+    print("# ncu --set full (--clock-control none) of the three sweep kernels, %d cells, one launch each\n" % cells)
     for r in rows[2:]:
         name = short(r[hdr.index("Kernel Name")])
         print("## %s\n" % name)
@@ -97,9 +100,15 @@ def full(path):
             return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
         axis = "x" if "sweep_x" in name else ("y" if "(y" in name else "z")
         traffic[axis] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-    json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"))
-    print("DRAM bytes per launch (read+write) -> profiles/traffic.json:", traffic)
+    if write_traffic:
+        traffic["cells"] = cells
+        traffic["source"] = "profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % os.path.basename(path)
+        json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
+    print("DRAM bytes per launch (read+write)%s:" % (" -> profiles/traffic.json" if write_traffic else ""), traffic)
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:       # full REPORT [cells] [notraffic]
+        full(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 512 ** 3, "notraffic" not in sys.argv)
