@@ -683,13 +683,15 @@ z_fused(const double *__restrict__ data, const double *__restrict__ Tin, double 
   auto y_get = [&](const double *q, bool own) {
     double x = __ldcg(q);
     if (!own && !dead) {
+      unsigned ns = 256;                 // back off: tens of thousands of threads polling L2 every 64 ns starve the data traffic
       while (__double_as_longlong(x) == (long long)HS2_Y_EMPTY) {
         if (clock64() - t_begin > max_cycles) {
           atomicExch(status, 1);
           dead = true;
           break;
         }
-        __nanosleep(64);
+        __nanosleep(ns);
+        if (ns < 4096) ns <<= 1;
         x = __ldcg(q);
       }
     }
@@ -875,13 +877,15 @@ z_fused_warp(const double *__restrict__ data, const double *__restrict__ Tin, do
         const double *s0 = Yc + (int64_t)(2 * q) * n_lines, *s1 = s0 + n_lines;
         y_f = __ldcg(s0), y_l = __ldcg(s1);
         if (live && !dead) {
+          unsigned ns = 256;             // back off: a warp's 32 lanes x 16 warps x 148 SMs polling every 64 ns flood L2
           while (__double_as_longlong(y_f) == (long long)HS2_Y_EMPTY || __double_as_longlong(y_l) == (long long)HS2_Y_EMPTY) {
             if (clock64() - t_begin > max_cycles) {
               atomicExch(status, 1);
               dead = true;
               break;
             }
-            __nanosleep(64);
+            __nanosleep(ns);
+            if (ns < 4096) ns <<= 1;
             y_f = __ldcg(s0), y_l = __ldcg(s1);
           }
         }
