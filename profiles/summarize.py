@@ -102,7 +102,7 @@ def full(path, cells=512 ** 3, write_traffic=True):
         traffic[axis] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
     if write_traffic:
         traffic["cells"] = cells
-        traffic["source"] = "profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % os.path.basename(path)
+        traffic["source"] = "gpurun_out/%s, summarised in profiles/kernels_r02.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % os.path.basename(path)
         json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
     print("DRAM bytes per launch (read+write)%s:" % (" -> profiles/traffic.json" if write_traffic else ""), traffic)
 
