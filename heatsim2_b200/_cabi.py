@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HS2_B200_LIB") or os.path.join(_PKG, "libhs2b200.so")
 
 HS2_COEF_STRIDE = 8
 HS2_LU_STRIDE = 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p = ctypes.c_void_p
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -91,6 +91,9 @@ PROTOTYPES = {
     "hs2_plan_last_kernel": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "hs2_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "hs2_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
+    "hs2_run_steps": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_void_p, ctypes.c_int,
+                                     c_void_p, c_void_p, ctypes.c_double, c_void_p, ctypes.c_int, c_void_p]),
+    "hs2_observe": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p, ctypes.c_double, c_void_p]),
     "hs2_sweep_x": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, c_void_p]),
     "hs2_sweep_x_part": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Source), c_void_p, c_void_p, ctypes.c_int,
                                         c_void_p]),

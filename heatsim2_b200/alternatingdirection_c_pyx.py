@@ -274,7 +274,7 @@ def run_adi_steps(ADI_params, ADI_steps, t, dt, Tarray, volumetric_elements, vol
 
 
 def run_adi_steps_n(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, volumetric, nsteps,
-                    probes=None, surface_dz=None, every=1):
+                    probes=None, surface_dz=None, every=1, use_graph=True):
     """``nsteps`` time steps with the field resident on the device and
     observation on the device (extension; the reference's demos copy the whole
     field to the host every step and index it there, demos/steelonfoam.py:132-143).
@@ -286,15 +286,83 @@ def run_adi_steps_n(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, 
     is evaluated on the device at the same instants.  Only the recorded values
     cross PCIe, once, at the end.
 
+    Runs of steps without an active volumetric source go to the library in ONE
+    call (``hs2_run_steps``: native loop, one observation kernel per recorded
+    instant, replayed as a CUDA graph unless ``use_graph`` is false); steps with
+    a source are taken one by one.
+
     Returns ``(T_final, record)`` with ``record = {"step": [...], "probes":
     ndarray [n_rec, n_probes], "surface": ndarray [n_rec, ny, nx]}`` (keys present
     when requested).  ``Tarray`` may be numpy (copied in once; result numpy) or a
     CUDA tensor (result CUDA tensor)."""
     import torch
-    from . import surface_temperature as st
     plan = ADI_params.plan
     if plan is None:
         raise RuntimeError("ADI_params carries no plan; it must come from heatsim2_b200.setup()")
+    nsteps, every = int(nsteps), int(every)
+    if every < 1:
+        raise ValueError("every must be >= 1")
+    if not hasattr(plan, "run_steps_device"):
+        return _run_adi_steps_n_stepwise(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, volumetric, nsteps,
+                                         probes, surface_dz, every)
+    was_numpy = not isinstance(Tarray, torch.Tensor)
+    plan.ensure_device(None if was_numpy or not Tarray.is_cuda else Tarray.device)
+    with torch.cuda.device(plan._dev):
+        if was_numpy:
+            cur = torch.empty(plan.shape, dtype=torch.float64, device=plan._dev)
+            plan.upload(Tarray, cur)
+        else:
+            if Tarray.dtype != torch.float64 or tuple(Tarray.shape) != plan.shape:
+                raise ValueError("Tarray must be float64 with the grid's shape %r" % (plan.shape,))
+            cur = Tarray.to(plan._dev).contiguous().clone()
+        nxt = torch.empty_like(cur)
+        n_rec = nsteps // every
+        cells = probe_rec = surf_rec = None
+        if probes:
+            nz, ny, nx = plan.shape
+            for (k, j, i) in probes:
+                if not (0 <= k < nz and 0 <= j < ny and 0 <= i < nx):
+                    raise IndexError("probe %r outside the grid %r" % ((k, j, i), plan.shape))
+            cells = torch.tensor([(k * ny + j) * nx + i for (k, j, i) in probes], dtype=torch.int64, device=plan._dev)
+            probe_rec = torch.zeros((n_rec, len(probes)), dtype=torch.float64, device=plan._dev)
+        if surface_dz is not None:
+            surf_rec = torch.zeros((n_rec,) + plan.shape[1:], dtype=torch.float64, device=plan._dev)
+        # bufs[n & 1] is the field before step n
+        bufs = [cur, nxt]
+        n = 0
+        while n < nsteps:
+            if plan.source_active(t0 + n * dt, volumetric):
+                run_adi_steps(ADI_params, ADI_steps, t0 + n * dt, dt, bufs[n & 1], volumetric_elements, volumetric,
+                              out=bufs[(n + 1) & 1])
+                n += 1
+                if n % every == 0:
+                    plan.observe(bufs[n & 1], cells, None if probe_rec is None else probe_rec[n // every - 1],
+                                 None if surf_rec is None else surf_rec[n // every - 1], surface_dz)
+                continue
+            m = n + 1
+            while m < nsteps and not plan.source_active(t0 + m * dt, volumetric):
+                m += 1
+            plan.run_steps_device(bufs[0], bufs[1], n, m - n, every, cells, probe_rec, surf_rec, surface_dz,
+                                  first_row=n // every, use_graph=use_graph)
+            n = m
+        final = bufs[nsteps & 1]
+        record = {"step": [(r + 1) * every for r in range(n_rec)]}
+        if probes:
+            record["probes"] = probe_rec.cpu().numpy()
+        if surface_dz is not None:
+            record["surface"] = surf_rec.cpu().numpy()
+        if was_numpy:
+            return plan.download(final), record
+        return final, record
+
+
+def _run_adi_steps_n_stepwise(ADI_params, ADI_steps, t0, dt, Tarray, volumetric_elements, volumetric, nsteps,
+                              probes, surface_dz, every):
+    """run_adi_steps_n for plans without the native loop (multi-GPU slab plans): one library call per step,
+    observation with tensor indexing."""
+    import torch
+    from . import surface_temperature as st
+    plan = ADI_params.plan
     was_numpy = not isinstance(Tarray, torch.Tensor)
     if was_numpy:
         plan.ensure_device()

@@ -66,6 +66,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
   // shared memory and every line is its own class - the whole-line global-memory kernels run all three sweeps
   if (desc->class_id_bytes == 4) p->d.flags |= HS2_FLAG_FORCE_FALLBACK;
   p->owned = nullptr;
+  p->graph_cache = nullptr;
   p->n = desc->nz * desc->ny * desc->nx;
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -84,6 +85,7 @@ int hs2_plan_create(const hs2_plan_desc *desc, hs2_plan **out) {
 }
 
 int hs2_plan_destroy(hs2_plan *plan) {
+  if (plan) hs2_graph_cache_free(plan);
   if (plan && plan->owned) hs2_owned_free(plan->owned);
   delete plan;
   return HS2_OK;
@@ -109,7 +111,7 @@ int hs2_plan_last_kernel(const hs2_plan *plan, int axis) {
 
 const char *hs2_kernel_name(int code) {
   static const char *const names[] = {"none", "whole-line", "tile", "tile-tma", "tile-tma-512", "tile-cpasync",
-                                      "tile-cpasync-512", "x-fold", "z-slab", "x-tma", "x-warp"};
+                                      "tile-cpasync-512", "x-fold", "z-slab", "x-tma", "x-warp", "tile-rows", "tile-rows-512"};
   return (code >= 0 && code < (int)(sizeof(names) / sizeof(names[0]))) ? names[code] : "?";
 }
 

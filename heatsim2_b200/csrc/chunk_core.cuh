@@ -118,8 +118,13 @@ __device__ __forceinline__ void chunk_backward_short(double (&v)[M], const doubl
 // the L1 data-pipe wavefronts of the y sweep and a third of the x sweep's.
 // Same values, same operation order => bit-identical to the table-load path.
 // (struct UTab: hs2_common.cuh)
-template <int M>
-__device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab &ut) {
+struct NoPace {
+  __device__ __forceinline__ void one() {}
+};
+// PACE: something with one() that is called once per two rows of the dependent chain (the persistent z kernel
+// issues the next tile's cp.async pieces there: the chain leaves the issue slots free)
+template <int M, class PACE>
+__device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab &ut, PACE &pace) {
 #pragma unroll
   for (int t = 0; t < M; ++t) v[t] *= ut.v[HS2_T_INV][t];
   double prev = 0.0;
@@ -127,6 +132,7 @@ __device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab
   for (int t = 0; t < M; ++t) {
     prev = fma(-ut.v[HS2_T_F][t], prev, v[t]);
     v[t] = prev;
+    if (t & 1) pace.one();
   }
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -135,6 +141,12 @@ __device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab
     a1 = fma(ut.v[HS2_T_C][t + 1], v[t + 1], a1);
   }
   return a0 + a1;
+}
+
+template <int M>
+__device__ __forceinline__ double chunk_forward_const(double (&v)[M], const UTab &ut) {
+  NoPace np;
+  return chunk_forward_const<M, NoPace>(v, ut, np);
 }
 
 template <int M>

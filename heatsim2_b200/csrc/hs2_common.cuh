@@ -24,7 +24,9 @@ struct hs2_plan {
   int last_kernel[3];  // HS2_K_* of the last sweep per axis (hs2_plan_last_kernel)
   UTab utab[3];        // copy of axis[a].h_utab (passed to the kernels by value)
   bool has_utab[3];
+  void *graph_cache;   // run_steps.cu: replay graph of the last hs2_run_steps configuration
 };
+void hs2_graph_cache_free(hs2_plan *plan);
 
 void hs2_set_error(const char *fmt, ...);
 

@@ -126,13 +126,54 @@ strided_sweep(double *__restrict__ data, const double *__restrict__ Tin, double 
 // (chunk_core.cuh).  Measured on B200 at 512^3 (scripts/ab_sweeps.py, one run): z sweep 0.641 -> 0.613 ms,
 // y sweep 0.377 -> 0.401 ms (it is HBM-bound already and the uniform loads add latency) - so UT is
 // instantiated for the z sweep only.
-template <int M, int W, bool FINAL, bool USE_TMA, bool BIG, bool UT>
+// The 16-byte cp.async pieces of one thread for one tile [L][W] (row r of the tile <- src + r * stride): thread tid
+// copies piece tid % (W/2) of rows tid / (W/2), + 2 nthr / W, ...  one() issues the next piece, rest() what is left
+// and closes the group; a default-constructed pacer does nothing.
+struct CpAsyncPacer {
+  const double *src = nullptr;
+  uint32_t dst = 0, dstep = 0;
+  int64_t sstep = 0;
+  int left = 0, ok = 0;
+  bool armed = false;
+  __device__ __forceinline__ void setup(const double *src0, const double *tile, int tid, int W, int nthr, int L, int64_t stride,
+                                        int lines_left) {
+    const int c = (tid % (W / 2)) * 2;
+    const int rstep = nthr / (W / 2);
+    const int r = tid / (W / 2);
+    ok = c < lines_left ? 16 : 0;
+    src = src0 + (int64_t)r * stride + (ok ? c : 0);
+    dst = smem_u32(tile + (size_t)r * W + c);
+    sstep = (int64_t)rstep * stride;
+    dstep = (uint32_t)rstep * (uint32_t)(W * 8);
+    left = r < L ? (L - r + rstep - 1) / rstep : 0;
+    armed = true;
+  }
+  __device__ __forceinline__ void one() {
+    if (left > 0) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok) : "memory");
+      src += sstep;
+      dst += dstep;
+      --left;
+    }
+  }
+  __device__ __forceinline__ void rest() {
+    if (!armed) return;
+    while (left > 0) one();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    armed = false;
+  }
+};
+
+// FETCH: how the next tile travels - 0: 16-byte cp.async pieces issued by every thread, 1: tensor boxes
+// (cp.async.bulk.tensor, one thread), 2: one bulk copy per row (cp.async.bulk, W * 8 bytes each, rows spread over the
+// block's threads; mbarrier completion like the boxes, no tensor map - the z sweep's rows lie a whole plane apart)
+template <int M, int W, bool FINAL, int FETCH, bool BIG, bool UT, bool AHEAD>
 __global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 2)
 strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ UTab ut,
                   const uint8_t *__restrict__ ucode, double *__restrict__ data, const double *__restrict__ Tin,
                   double *__restrict__ Tout, const uint32_t *__restrict__ line_id, const double *__restrict__ tab,
                   const double *__restrict__ GE, int L, int pitch, int P, int band, int64_t stride, int tiles_per_group,
-                  int lines_per_group, int64_t group_stride, int n_tiles, int BR, int n_boxes, int do_prefetch) {
+                  int lines_per_group, int64_t group_stride, int n_tiles, int BR, int n_boxes, int do_prefetch, int pace) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double *tile = reinterpret_cast<double *>(smraw);              // [n_boxes*BR][W]
   double *Y = tile + (size_t)n_boxes * BR * W;                     // [2P][W]
@@ -140,6 +181,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   uint64_t *bar = reinterpret_cast<uint64_t *>(Es + P * W);
   double *s_tab = reinterpret_cast<double *>(bar + 2);             // [HS2_T_PLANES][pitch] of one unique line
   double *s_ge = s_tab + HS2_T_PLANES * pitch;                     // [P][2P]
+  constexpr bool USE_TMA = FETCH != 0;                             // completion through the mbarrier
   const int w = threadIdx.x;
   const int p = threadIdx.y;
   const bool leader = (w == 0 && p == 0);
@@ -160,7 +202,7 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   auto issue = [&](int t) {
     const int group = t / tiles_per_group;
     const int c0 = (t % tiles_per_group) * W;
-    if (USE_TMA) {
+    if (FETCH == 1) {
       if (!leader) return;
       mbar_expect_tx(bar, tile_bytes);
       for (int b = 0; b < n_boxes; ++b) {
@@ -169,19 +211,26 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         else                // z-sweep: (flattened line, row, 0)
           tma_load_3d(tile + (size_t)b * BR * W, &tmap, bar, c0, b * BR, 0);
       }
-    } else {
+    } else if (FETCH == 2) {
       const int nthr = W * P;
       const int tid = threadIdx.y * W + w;
-      const double *src0 = data + (int64_t)group * group_stride + c0;
-      for (int e = tid; e < L * (W / 2); e += nthr) {
-        const int r = e / (W / 2), c = (e % (W / 2)) * 2;
-        const int ok = (c0 + c < lines_per_group) ? 16 : 0;
-        const double *src = src0 + (int64_t)r * stride + (ok ? c : 0);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(tile + (size_t)r * W + c)), "l"(src),
-                     "r"(ok)
+      const uint32_t row_bytes = (uint32_t)min(W, lines_per_group - c0) * 8u;
+      if (leader) mbar_expect_tx(bar, row_bytes * (uint32_t)L);
+      const double *src = data + (int64_t)group * group_stride + c0 + (int64_t)tid * stride;
+      uint32_t dst = smem_u32(tile) + (uint32_t)tid * (W * 8);
+      const int64_t sstep = (int64_t)nthr * stride;
+      for (int r = tid; r < L; r += nthr) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(row_bytes), "r"(smem_u32(bar))
                      : "memory");
+        src += sstep;
+        dst += (uint32_t)nthr * (W * 8);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+      // thread tid copies the 16-byte piece (tid % (W/2)) of rows tid / (W/2), + 2 nthr / W, ...
+      CpAsyncPacer pc;
+      pc.setup(data + (int64_t)group * group_stride + c0, tile, threadIdx.y * W + w, W, W * P, L, stride, lines_per_group - c0);
+      pc.rest();
     }
   };
   int t = blockIdx.x;
@@ -201,23 +250,48 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   }
   __syncthreads();
   uint32_t parity = 0;
+  // AHEAD: the unique-line id of this thread's line (and, in the z sweep, the common-table code that depends on it)
+  // are fetched one tile ahead, so that the two dependent global loads are off the critical path of the tile.
+  // Measured on B200: z sweep 0.634 -> 0.571 ms at 512^3 together with the lean T_in addressing; y sweep with several
+  // line classes (steelonwater 512^3) 0.444 -> 0.411 ms; but the y sweep of one-class grids LOSES (the two registers
+  // push the 128-register kernel into spills: 256-row lines 0.394 -> 0.438 ms, 1024-row lines 0.367 -> 0.434 ms), so
+  // the launcher sets AHEAD for the z sweep and for y sweeps over more than one line class only.
+  auto line_of = [&](int tt) {
+    const int cc = (tt % tiles_per_group) * W + w;
+    return (int64_t)(tt / tiles_per_group) * lines_per_group + (cc < lines_per_group ? cc : 0);
+  };
+  const bool has_ucode = UT && ucode != nullptr;
+  uint32_t lid_n = (AHEAD && t < n_tiles) ? line_id[line_of(t)] : 0u;
+  uint8_t uc_n = (AHEAD && has_ucode && t < n_tiles) ? ucode[(int64_t)lid_n * P + p] : (uint8_t)0;
   for (; t < n_tiles; t += gridDim.x) {
     const int group = t / tiles_per_group;
     const int col = (t % tiles_per_group) * W + w;
     const bool live = col < lines_per_group;
-    const int64_t line = (int64_t)group * lines_per_group + (live ? col : 0);
     const int64_t off = (int64_t)group * group_stride + (live ? col : 0) + (int64_t)r0 * stride;
-    const uint32_t lid = line_id[line];
+    const uint32_t lid = AHEAD ? lid_n : line_id[line_of(t)];
     // every chunk of this warp carries the axis' common table: factors come from the constant bank
-    const bool uni = UT && ucode != nullptr && __all_sync(0xffffffffu, ucode[(int64_t)lid * P + p] != 0);
+    const bool uni = has_ucode && __all_sync(0xffffffffu, (AHEAD ? uc_n : ucode[(int64_t)lid * P + p]) != 0);
+    const bool more = t + (int)gridDim.x < n_tiles;
+    if (AHEAD && more) lid_n = line_id[line_of(t + gridDim.x)];
     const double *tb = lid == lid_c ? s_tab + r0 : tab + ((int64_t)lid * HS2_T_PLANES) * pitch + r0;
     const double *ge = lid == lid_c ? s_ge + p * (2 * P) : GE + ((int64_t)lid * P + p) * (2 * P);
+    const int64_t sbytes = stride * (int64_t)sizeof(double);
     if (FINAL && live && do_prefetch && (w & 3) == 0) {
-      // warm L2 with the T_in rows this tile adds at the end (one lane per 32-byte sector)
-      const double *ti = Tin + off;
+      // warm L2 with the T_in rows this tile adds at the end (one lane per 32-byte sector); addresses by pointer
+      // increments: base + q * stride with a 64-bit run-time stride cost ~20 instructions per row
+      const char *ti = reinterpret_cast<const char *>(Tin + off);
+      if (full) {
 #pragma unroll
-      for (int q = 0; q < M; ++q)
-        if (q < rows) prefetch_l2(ti + (int64_t)q * stride);
+        for (int q = 0; q < M; ++q) {
+          prefetch_l2(ti);
+          ti += sbytes;
+        }
+      } else {
+        for (int q = 0; q < rows; ++q) {
+          prefetch_l2(ti);
+          ti += sbytes;
+        }
+      }
     }
     HS2_MARK(8);
     if (USE_TMA) {
@@ -236,12 +310,25 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
     HS2_MARK(1);
     __syncthreads();                       // tile buffer is free again
-    if (t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+    // next tile: the copy engines get it at once; the cp.async pieces either in one go or (pace) one piece per
+    // two rows of the forward elimination's dependent chain - free issue slots, and no burst of 4096 pieces per
+    // block queueing ahead of the other resident block's T_in loads
+    CpAsyncPacer pacer;
+    if (more) {
+      if (FETCH == 0 && pace) {
+        const int tn = t + gridDim.x;
+        const int c0n = (tn % tiles_per_group) * W;
+        pacer.setup(data + (int64_t)(tn / tiles_per_group) * group_stride + c0n, tile, threadIdx.y * W + w, W, W * P, L, stride,
+                    lines_per_group - c0n);
+      } else {
+        issue(t + gridDim.x);
+      }
+    }
     HS2_MARK(2);
     // (16-byte table loads: the 8-byte variant of chunk_core.cuh measured 6 % slower here)
     double yf, last;
     if (UT && uni) {
-      yf = chunk_forward_const<M>(v, ut);
+      yf = chunk_forward_const<M>(v, ut, pacer);
       last = v[M - 1];
     } else if (full) {
       yf = chunk_forward_full<M>(v, tb, pitch);
@@ -249,12 +336,14 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     } else {
       yf = chunk_forward_short<M>(v, tb, pitch, rows, &last);
     }
+    pacer.rest();
     Y[(2 * p) * W + w] = yf;
     Y[(2 * p + 1) * W + w] = last;
     HS2_MARK(3);
     __syncthreads();
     const double E = chunk_interface(ge, Y, P, W, w, p, band);
     Es[p * W + w] = E;
+    if (AHEAD && more && has_ucode) uc_n = ucode[(int64_t)lid_n * P + p];       // lid_n arrived long ago
     HS2_MARK(4);
     __syncthreads();
     const double alpha = p > 0 ? Es[(p - 1) * W + w] : 0.0;
@@ -269,22 +358,47 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if (FINAL) {
         // T_in in batches of 8 rows, software-pipelined: the loads of batch g+1
         // are in flight while batch g is added and stored
-        const double *ti = Tin + off;
-        double *to = Tout + off;
         // (requesting the first batch before the back substitution measured slower: 0.68 vs 0.63 ms)
         double tin[2][8];
+        if (full) {
+          const char *ti = reinterpret_cast<const char *>(Tin + off);
+          char *to = reinterpret_cast<char *>(Tout + off);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) tin[0][q] = (q < rows) ? ti[(int64_t)q * stride] : 0.0;
-#pragma unroll
-        for (int g = 0; g < M; g += 8) {
-          if (g + 8 < M) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              tin[((g >> 3) + 1) & 1][q] = (g + 8 + q < rows) ? ti[(int64_t)(g + 8 + q) * stride] : 0.0;
+          for (int q = 0; q < 8; ++q) {
+            tin[0][q] = *reinterpret_cast<const double *>(ti);
+            ti += sbytes;
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (g + q < rows) to[(int64_t)(g + q) * stride] = tin[(g >> 3) & 1][q] + v[g + q];
+          for (int g = 0; g < M; g += 8) {
+            if (g + 8 < M) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                tin[((g >> 3) + 1) & 1][q] = *reinterpret_cast<const double *>(ti);
+                ti += sbytes;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              *reinterpret_cast<double *>(to) = tin[(g >> 3) & 1][q] + v[g + q];
+              to += sbytes;
+            }
+          }
+        } else {
+          const double *ti = Tin + off;
+          double *to = Tout + off;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tin[0][q] = (q < rows) ? ti[(int64_t)q * stride] : 0.0;
+#pragma unroll
+          for (int g = 0; g < M; g += 8) {
+            if (g + 8 < M) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                tin[((g >> 3) + 1) & 1][q] = (g + 8 + q < rows) ? ti[(int64_t)(g + 8 + q) * stride] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (g + q < rows) to[(int64_t)(g + q) * stride] = tin[(g >> 3) & 1][q] + v[g + q];
+          }
         }
       } else {
         double *dst = data + off;
@@ -318,12 +432,17 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   // row); measured on B200 the tensor copy engine then delivers < half the
   // bandwidth of plain loads (profiles/NOTES_r01.md), so the z-sweep keeps the
   // register-load kernel unless HS2_TMA_Z=1.
-  // HS2_Z_PREFETCH: 0 = register-load kernel, 1 = cp.async persistent kernel (default), 2 = TMA
+  // HS2_Z_PREFETCH: 0 = register-load kernel, 1 = cp.async persistent kernel (default), 2 = TMA boxes, 3 = bulk rows
   static const int zmode = getenv("HS2_Z_PREFETCH") ? atoi(getenv("HS2_Z_PREFETCH")) : 1;
   if (group_stride == 0 && zmode == 0) return HS2_OK;
   const bool use_tma = group_stride != 0 || zmode == 2;
+  const bool use_rows = group_stride == 0 && zmode == 3 && !(lines_per_group & 1) && !(stride & 1) &&
+                        !(reinterpret_cast<uintptr_t>(data) & 15);
   const uint8_t *ucode = (FINAL && pl->has_utab[axis] && !(pl->d.flags & HS2_FLAG_NO_UTAB)) ? ax.d_ucode : nullptr;
-  static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 1;
+  // L2 warm-up of the tile's T_in rows at tile start: off since the T_in / store phase addresses its rows by pointer
+  // increments (measured at 512^3: z sweep 0.630 ms with it, 0.571 ms without; 256^3: 0.080 / 0.078)
+  static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 0;
+  static const int pace = getenv("HS2_Z_PACE") ? atoi(getenv("HS2_Z_PACE")) : 1;
   const int BR = L < 256 ? L : 256;
   const int n_boxes = (L + BR - 1) / BR;
   const size_t smem = ((size_t)n_boxes * BR * W + 3 * (size_t)P * W + (size_t)HS2_T_PLANES * ax.pitch + 2 * (size_t)P * P) * sizeof(double) + 16;
@@ -345,31 +464,41 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   const int carveout = carveout_env >= 0 ? carveout_env : (int)((bps * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  if (use_tma) {
+  // (the last template flag, AHEAD: see the kernel - always in the z sweep, in the y sweep for several line classes)
+  auto kern = big ? strided_sweep_tma<M, W, FINAL, 0, (M >= 32), FINAL, FINAL> : strided_sweep_tma<M, W, FINAL, 0, false, FINAL, FINAL>;
+  bool rows = false;
+  if constexpr (FINAL) {
+    if (use_rows) {
+      kern = big ? strided_sweep_tma<M, W, FINAL, 2, (M >= 32), FINAL, FINAL> : strided_sweep_tma<M, W, FINAL, 2, false, FINAL, FINAL>;
+      rows = true;
+    }
+  }
+  if (rows) {
+    pl->last_kernel[axis] = big ? HS2_K_TILE_ROWS_BIG : HS2_K_TILE_ROWS;
+  } else if (use_tma) {
     bool ok;
     if (group_stride)
       ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, (uint64_t)n_groups, W, BR, 1);
     else
       ok = hs2_encode_tmap_f64_3d(&tmap, data, (uint64_t)lines_per_group, (uint64_t)L, 1, W, BR, 1);
     if (!ok) return HS2_OK;
-    auto kern = big ? strided_sweep_tma<M, W, FINAL, true, (M >= 32), FINAL> : strided_sweep_tma<M, W, FINAL, true, false, FINAL>;
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
-    kern<<<grid, block, smem, st>>>(tmap, pl->utab[axis], ucode, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
-                                    stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
+    kern = big ? strided_sweep_tma<M, W, FINAL, 1, (M >= 32), FINAL, FINAL> : strided_sweep_tma<M, W, FINAL, 1, false, FINAL, FINAL>;
+    if constexpr (!FINAL) {
+      static const int ahead_env = getenv("HS2_Y_AHEAD") ? atoi(getenv("HS2_Y_AHEAD")) : -1;
+      const bool ahead = ahead_env >= 0 ? ahead_env != 0 : (ax.n_unique > 1 && P == 16);
+      if (ahead && !big) kern = strided_sweep_tma<M, W, FINAL, 1, false, FINAL, true>;
+    }
     pl->last_kernel[axis] = big ? HS2_K_TILE_TMA_BIG : HS2_K_TILE_TMA;
   } else {
     // 16-byte cp.async pieces: every row start must be 16-byte aligned
     if ((lines_per_group & 1) || (stride & 1) || (group_stride & 1) || (reinterpret_cast<uintptr_t>(data) & 15)) return HS2_OK;
-    auto kern = big ? strided_sweep_tma<M, W, FINAL, false, (M >= 32), FINAL> : strided_sweep_tma<M, W, FINAL, false, false, FINAL>;
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
-    HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
-    kern<<<grid, block, smem, st>>>(tmap, pl->utab[axis], ucode, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
-                                    stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf);
     pl->last_kernel[axis] = big ? HS2_K_TILE_CPASYNC_BIG : HS2_K_TILE_CPASYNC;
   }
+  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // two blocks per SM: leave the rest of the 256 KB array to L1 (factor tables live there)
+  HS2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout));
+  kern<<<grid, block, smem, st>>>(tmap, pl->utab[axis], ucode, data, Tin, Tout, ax.d_line_id, ax.d_tab, ax.d_GE, L, ax.pitch, P, ax.band,
+                                  stride, tiles_per_group, lines_per_group, group_stride, (int)n_tiles, BR, n_boxes, pf, pace);
   HS2_CUDA_CHECK(cudaGetLastError());
   *done = true;
   return HS2_OK;
@@ -463,10 +592,14 @@ z_forward(const double *__restrict__ data, const uint32_t *__restrict__ line_id,
     if (tile + g >= n_tiles || rel >= n_lines) continue;
     const int col = line0 + rel;
     const uint32_t lid = line_id[col];
-    const double *ptr = data + col + (int64_t)p * M * stride;
+    const char *ptr = reinterpret_cast<const char *>(data + col + (int64_t)p * M * stride);
+    const int64_t sbytes = stride * (int64_t)sizeof(double);     // rows by pointer increments (no 64-bit multiply per row)
     double v[M];
 #pragma unroll
-    for (int t = 0; t < M; ++t) v[t] = ptr[(int64_t)t * stride];
+    for (int t = 0; t < M; ++t) {
+      v[t] = *reinterpret_cast<const double *>(ptr);
+      ptr += sbytes;
+    }
     // the eliminated chunk is NOT written back: z_backward repeats the (cheap)
     // forward elimination from the same input instead of re-reading 8 B/cell
     double yf, last;
@@ -527,9 +660,16 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
     const uint32_t lid = line_id[col];
     const bool tab_s = lid == lid_c;
     const int64_t off = col + (int64_t)p * M * stride;
+    const int64_t sbytes = stride * (int64_t)sizeof(double);     // rows by pointer increments (no 64-bit multiply per row)
     double v[M];
+    {
+      const char *ptr = reinterpret_cast<const char *>(data + off);
 #pragma unroll
-    for (int t = 0; t < M; ++t) v[t] = data[off + (int64_t)t * stride];
+      for (int t = 0; t < M; ++t) {
+        v[t] = *reinterpret_cast<const double *>(ptr);
+        ptr += sbytes;
+      }
+    }
     // rows pg (-> E) and pg-1 (-> alpha) of the inverse interface operator
     double E = 0.0, alpha = 0.0;
     const double *Yc = Yall + ycol0 + rel;               // this line's column of the interface rows [2 P_glob][ldy]
@@ -568,16 +708,27 @@ z_backward(const double *__restrict__ data, const double *__restrict__ Tin, doub
     // T_in in batches of 8 rows, software-pipelined: the loads of batch g+1 are
     // in flight while batch g is added and stored
     double tin[2][8];
+    const char *ti = reinterpret_cast<const char *>(Tin + off);
+    char *to = reinterpret_cast<char *>(Tout + off);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) tin[0][q] = Tin[off + (int64_t)q * stride];
+    for (int q = 0; q < 8; ++q) {
+      tin[0][q] = *reinterpret_cast<const double *>(ti);
+      ti += sbytes;
+    }
 #pragma unroll
     for (int gb = 0; gb < M; gb += 8) {
       if (gb + 8 < M) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) tin[((gb >> 3) + 1) & 1][q] = Tin[off + (int64_t)(gb + 8 + q) * stride];
+        for (int q = 0; q < 8; ++q) {
+          tin[((gb >> 3) + 1) & 1][q] = *reinterpret_cast<const double *>(ti);
+          ti += sbytes;
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) Tout[off + (int64_t)(gb + q) * stride] = tin[(gb >> 3) & 1][q] + v[gb + q];
+      for (int q = 0; q < 8; ++q) {
+        *reinterpret_cast<double *>(to) = tin[(gb >> 3) & 1][q] + v[gb + q];
+        to += sbytes;
+      }
     }
   }
 }

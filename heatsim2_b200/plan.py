@@ -653,6 +653,22 @@ class AdiPlan(object):
             src.d_dense = d.data_ptr()
         return src, keep
 
+    @staticmethod
+    def source_active(t, volumetric):
+        """True when a step taken at time ``t`` may carry a volumetric source (the time conditions of
+        ``evaluate_sources`` / alternatingdirection_c_pyx.pyx:301-383, without touching any array)."""
+        from . import NO_SOURCE, STEPPED_SOURCE
+        for entry in (volumetric if volumetric is not None else ()):
+            kind = entry[0]
+            if kind == NO_SOURCE:
+                continue
+            if kind == STEPPED_SOURCE:
+                if t >= entry[1] and t <= entry[2]:
+                    return True
+            elif t == entry[1]:      # the three impulse kinds fire at exactly t == t_impulse
+                return True
+        return False
+
     def evaluate_sources(self, t, dt, volumetric_elements, volumetric):
         """Evaluate the volumetric sources active at time ``t`` (reference
         alternatingdirection_c_pyx.pyx:294-386) on the host.  Returns
@@ -748,6 +764,68 @@ class AdiPlan(object):
         if keep is not None and len(keep) > 1:
             torch.cuda.current_stream(self._dev).synchronize()    # dense source buffer must outlive the launch
         return T_out
+
+    # ------------------------------------------- many steps per call, observation on the device
+    def observe(self, T, cells, probe_out, surface_out, dz):
+        """hs2_observe: probe cells (flat int64 indices, device) and / or the insulated z-min surface temperature
+        (reference heatsim2/surface_temperature.py:4-36) of the device field ``T`` into device tensors."""
+        lib = _cabi.lib()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+        use_p = cells is not None and probe_out is not None
+        _cabi.check(lib.hs2_observe(self._handle, T.data_ptr(), cells.data_ptr() if use_p else None,
+                                    cells.numel() if use_p else 0, probe_out.data_ptr() if use_p else None,
+                                    surface_out.data_ptr() if surface_out is not None else None,
+                                    float(dz) if dz is not None else 0.0, stream))
+
+    def run_steps_device(self, T_even, T_odd, first_step, nsteps, every=1, cells=None, probe_rec=None, surf_rec=None,
+                         dz=None, first_row=0, use_graph=True):
+        """hs2_run_steps: the source-free steps ``first_step .. first_step + nsteps - 1`` in one library call.
+        Step n reads ``T_even`` for even n, ``T_odd`` for odd n, and writes the other tensor; after every step with
+        ``(n + 1) % every == 0`` the probes / surface estimate go to row ``first_row, first_row + 1, ...`` of the
+        record tensors.  Asynchronous on the current stream."""
+        self.ensure_device(T_even.device)
+        for T in (T_even, T_odd):
+            self._check_field(T)
+            if T.dtype != torch.float64 or not T.is_contiguous() or T.device != T_even.device:
+                raise ValueError("run_steps_device: fields must be contiguous float64 tensors on one device")
+        lib = _cabi.lib()
+        work = self._buf("work")
+        counter = self._bufs.get("row_counter")
+        if counter is None:
+            counter = self._bufs["row_counter"] = torch.zeros(1, dtype=torch.int64, device=self._dev)
+        use_p = cells is not None and probe_rec is not None
+        if use_p or surf_rec is not None:
+            counter.fill_(int(first_row))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+        _cabi.check(lib.hs2_run_steps(self._handle, T_even.data_ptr(), T_odd.data_ptr(), work.data_ptr(), int(first_step),
+                                      int(nsteps), int(every), cells.data_ptr() if use_p else None,
+                                      cells.numel() if use_p else 0, probe_rec.data_ptr() if use_p else None,
+                                      surf_rec.data_ptr() if surf_rec is not None else None,
+                                      float(dz) if dz is not None else 0.0, counter.data_ptr(), 1 if use_graph else 0, stream))
+
+    def upload(self, array, dev):
+        """numpy array (or host tensor) -> device tensor ``dev`` at full PCIe speed: page-locked sources by one DMA,
+        pageable ones through the pinned staging chunks."""
+        arr = np.ascontiguousarray(_to_numpy(array), dtype=np.float64)
+        self._check_field(arr)
+        h = torch.from_numpy(arr)
+        if h.is_pinned():
+            dev.copy_(h, non_blocking=True)
+            torch.cuda.current_stream(self._dev).synchronize()
+        else:
+            self._upload(h, dev)
+        return dev
+
+    def download(self, dev):
+        """device tensor -> new numpy array (page-locked unless HS2_PINNED_RESULTS=0, like ``run_step``'s results)"""
+        if os.environ.get("HS2_PINNED_RESULTS", "1") != "0":
+            result = torch.empty(tuple(dev.shape), dtype=torch.float64, pin_memory=True)
+            result.copy_(dev, non_blocking=True)
+            torch.cuda.current_stream(self._dev).synchronize()
+        else:
+            result = torch.empty(tuple(dev.shape), dtype=torch.float64)
+            self._download(dev, result)
+        return result.numpy()
 
     def _check_field(self, T):
         if tuple(T.shape) != self.shape:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HS2_ABI_VERSION 5
+#define HS2_ABI_VERSION 6
 
 #define HS2_OK 0
 #define HS2_E_INVALID (-1) /* bad argument / unsupported shape               */
@@ -243,6 +243,8 @@ int hs2_plan_x_kernel(const hs2_plan *plan);
 #define HS2_K_Z_SLAB 8         /* z_forward / z_backward of a slab plan                  */
 #define HS2_K_X_TMA 9          /* sweep_xt_kernel: patches staged by TMA, chunk-layout RHS */
 #define HS2_K_X_WARP 10        /* sweep_xw_kernel: one warp per line, interfaces by shuffle */
+#define HS2_K_TILE_ROWS 11     /* persistent, next tile by one bulk copy per row         */
+#define HS2_K_TILE_ROWS_BIG 12
 int hs2_plan_last_kernel(const hs2_plan *plan, int axis);
 const char *hs2_kernel_name(int code);
 
@@ -256,6 +258,26 @@ const char *hs2_kernel_name(int code);
 int hs2_step(hs2_plan *plan, const double *d_T_in, double *d_T_out,
              double *d_work, const hs2_source *src, const double *d_halo_lo,
              const double *d_halo_hi, void *stream);
+
+/* Many steps per call, field resident in HBM (the reference's demos call run_adi_steps once per step from Python and
+ * copy the whole field back to index it: demos/steelonfoam.py:132-143, demos/ktest.py).  Runs the source-free steps
+ * first_step .. first_step + nsteps - 1: step n reads d_T_a for even n and d_T_b for odd n and writes the other
+ * buffer.  After every step with (n + 1) % every == 0 the observation of hs2_observe is appended to the record
+ * arrays at row *d_counter (a 64-bit device word the caller owns and sets to the first free row; it is incremented
+ * on the device after each record, so that the launches can be replayed):
+ *   d_probe_rec   [rows][n_probes]  or NULL      d_surface_rec [rows][ny][nx]  or NULL
+ * use_graph != 0: a unit of steps is captured once into a CUDA graph (kept by the plan for the next call with the
+ * same buffers) and replayed - no per-launch cost on small grids; 0: plain launches.  Asynchronous on `stream`.  */
+int hs2_run_steps(hs2_plan *plan, double *d_T_a, double *d_T_b, double *d_work, int64_t first_step, int64_t nsteps,
+                  int every, const int64_t *d_probe_cells, int n_probes, double *d_probe_rec, double *d_surface_rec,
+                  double dz, uint64_t *d_counter, int use_graph, void *stream);
+/* Observation of one field on the device, one launch:
+ *   d_probe_out[q]      = T[d_probe_cells[q]]   (flat cell index (k*ny + j)*nx + i), q < n_probes
+ *   d_surface_out[j][i] = the insulated z-min surface temperature estimated from planes 0 and 1,
+ *                         heatsim2/surface_temperature.py:4-36 (same operations in the same order)
+ * Either output may be NULL.                                                                                       */
+int hs2_observe(hs2_plan *plan, const double *d_T, const int64_t *d_probe_cells, int n_probes, double *d_probe_out,
+                double *d_surface_out, double dz, void *stream);
 
 /* The three stages separately (multi-GPU drivers interleave communication).
  * hs2_sweep_x: d_work = (M - Lx/2)^-1 [(Lx+Ly+Lz) T_in + D src]

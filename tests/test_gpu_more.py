@@ -118,6 +118,50 @@ def test_device_resident_loop_with_observation(hs):
     assert util.relerr(rec["surface"][-1], want_surface) <= 1e-14
 
 
+@pytest.mark.parametrize("every,nsteps,use_graph", [(1, 23, True), (3, 40, True), (4, 40, True), (3, 40, False)])
+def test_native_step_loop_equals_stepwise(hs, every, nsteps, use_graph):
+    """hs2_run_steps (native loop, CUDA-graph replay, device-side record counter) against one run_adi_steps call per
+    step: same kernels on the same data -> identical bits, whatever the recording period (odd periods replay two
+    periods per graph) and wherever steps with a source (taken one by one) cut the run into segments."""
+    import torch
+    prob = problems.sources_demo(hs)       # sources fire at steps 0, 1..3, 2, 3: the first native segment starts at 4
+    P, S = hs.setup(*prob["setup_args"])
+    ve, vol, dt, dz = prob["volumetric_elements"], prob["volumetric"], prob["dt"], prob["dz"]
+    probes = [(0, 0, 0), (5, 4, 3), (11, 9, 13)]
+    T = torch.from_numpy(np.array(prob["T0"])).cuda()
+    Tn, rec = hs.run_adi_steps_n(P, S, prob["t0"], dt, T, ve, vol, nsteps, probes=probes, surface_dz=dz, every=every,
+                                 use_graph=use_graph)
+    cur, want_p, want_s = T.clone(), [], []
+    for n in range(nsteps):
+        cur = hs.run_adi_steps(P, S, prob["t0"] + n * dt, dt, cur, ve, vol)
+        if (n + 1) % every == 0:
+            want_p.append([float(cur[p]) for p in probes])
+            # on numpy, like the reference (torch divides a tensor by a scalar as a multiplication by 1/scalar)
+            want_s.append(hs.surface_temperature.insulating_z_min_surface_temperature(cur.cpu().numpy(), dz))
+    assert rec["step"] == [(r + 1) * every for r in range(nsteps // every)]
+    assert np.array_equal(Tn.cpu().numpy(), cur.cpu().numpy())
+    assert np.array_equal(rec["probes"], np.array(want_p))
+    assert np.array_equal(rec["surface"], np.array(want_s))
+    # the caller's tensor is left alone, and a second call (cached graph, other record buffers) gives the same
+    assert np.array_equal(T.cpu().numpy(), np.array(prob["T0"]))
+    Tn2, rec2 = hs.run_adi_steps_n(P, S, prob["t0"], dt, T, ve, vol, nsteps, probes=probes, surface_dz=dz, every=every,
+                                   use_graph=use_graph)
+    assert np.array_equal(Tn2.cpu().numpy(), Tn.cpu().numpy()) and np.array_equal(rec2["surface"], rec["surface"])
+
+
+def test_native_step_loop_source_free_numpy(hs):
+    """no sources at all: the whole run is one hs2_run_steps call (graph units + remainder); numpy in, numpy out"""
+    import adi_oracle
+    prob = problems.uniform_slab(hs, shape=(24, 20, 32), nsteps=37)
+    P, S = hs.setup(*prob["setup_args"])
+    Tn, rec = hs.run_adi_steps_n(P, S, prob["t0"], prob["dt"], prob["T0"], prob["volumetric_elements"], prob["volumetric"],
+                                 37, probes=[(3, 2, 1)], every=5)
+    assert isinstance(Tn, np.ndarray) and rec["probes"].shape == (7, 1) and "surface" not in rec
+    want = adi_oracle.run(prob, nsteps=37)
+    assert util.relerr(Tn, want) <= 1e-11
+    assert abs(rec["probes"][-1, 0] - adi_oracle.run(prob, nsteps=35)[3, 2, 1]) <= 1e-11 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("name,kwargs,world,nsteps", [
     ("steelonfoam", dict(nz=64, ny=40, nx=48), 2, 6),
     ("uniform_slab", dict(shape=(128, 48, 64)), 4, 4),

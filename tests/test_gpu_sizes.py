@@ -178,8 +178,13 @@ def test_survey_sizes_vs_reference_digests(hs, case):
                          prob["volumetric"], out=nxt)
         T, nxt = nxt, T
         if cols:
-            # C4: surface temperature evaluated on the device tensor every step
-            surf = hs.surface_temperature.insulating_z_min_surface_temperature(T, prob["dz"])
+            # C4: surface temperature evaluated on the device tensor every step, by the library's
+            # observation kernel (hs2_observe), which must give the bits of the reference's formula
+            surf = torch.empty(T.shape[1:], dtype=T.dtype, device=T.device)
+            P.plan.observe(T, None, None, surf, prob["dz"])
+            if it % 50 == 0:
+                assert np.array_equal(surf.cpu().numpy(), hs.surface_temperature.insulating_z_min_surface_temperature(
+                    T.cpu().numpy(), prob["dz"]))      # numpy, like the reference: true division
             hist.append(torch.stack([surf[tuple(c)] for c in cols]))
         if (it + 1) in meta["steps"]:
             tol = TOL_STEP if it == 0 else TOL_RUN
