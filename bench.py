@@ -398,14 +398,20 @@ def run_b200_single(args):
     try:
         n_res = 50
         h_np = A
-        torch.cuda.synchronize()
-        t0w = time.perf_counter()
-        T_fin, rec = hs.run_adi_steps_n(P, S, it * dt, dt, h_np, ve, vol, n_res, probes=[(0, 1, 1), (shape[0] // 2, 2, 3)])
-        torch.cuda.synchronize()
-        res_ms = (time.perf_counter() - t0w) * 1e3 / n_res
+        res_ms_calls = []
+        for _call in range(2):      # the first call page-locks the 1 GB result buffer (a one-off ~0.4 s); report the second
+            torch.cuda.synchronize()
+            t0w = time.perf_counter()
+            T_fin, rec = hs.run_adi_steps_n(P, S, it * dt, dt, h_np, ve, vol, n_res, probes=[(0, 1, 1), (shape[0] // 2, 2, 3)])
+            torch.cuda.synchronize()
+            res_ms_calls.append((time.perf_counter() - t0w) * 1e3 / n_res)
+            h_np = T_fin
+        res_ms = res_ms_calls[-1]
         e2e_resident = {"value": n / (res_ms * 1e-3), "unit": UNIT, "ms_per_step": res_ms, "steps_per_call": n_res,
+                        "first_call_ms_per_step": res_ms_calls[0],
                         "h2d_bytes_per_call": n * 8, "d2h_bytes_per_call": n * 8 + int(rec["probes"].nbytes),
-                        "api": "heatsim2_b200.run_adi_steps_n(numpy in, %d steps, probes on device, numpy out); wall clock" % n_res}
+                        "api": "heatsim2_b200.run_adi_steps_n(numpy in, %d steps in one hs2_run_steps call (CUDA-graph replay), "
+                               "probes recorded on the device, numpy out); wall clock of the second call" % n_res}
         del T_fin, rec
     except Exception as exc:          # informational figure: never let it take the bench line down
         e2e_resident = {"error": str(exc)[:200]}
