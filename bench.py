@@ -399,13 +399,14 @@ def run_b200_single(args):
         n_res = 50
         h_np = A
         res_ms_calls = []
+        T_fin = rec = None
         for _call in range(2):      # the first call page-locks the 1 GB result buffer (a one-off ~0.4 s); report the second
+            del T_fin, rec          # (the dropped result's page-locked block is what the second call's result re-uses)
             torch.cuda.synchronize()
             t0w = time.perf_counter()
             T_fin, rec = hs.run_adi_steps_n(P, S, it * dt, dt, h_np, ve, vol, n_res, probes=[(0, 1, 1), (shape[0] // 2, 2, 3)])
             torch.cuda.synchronize()
             res_ms_calls.append((time.perf_counter() - t0w) * 1e3 / n_res)
-            h_np = T_fin
         res_ms = res_ms_calls[-1]
         e2e_resident = {"value": n / (res_ms * 1e-3), "unit": UNIT, "ms_per_step": res_ms, "steps_per_call": n_res,
                         "first_call_ms_per_step": res_ms_calls[0],
