@@ -277,17 +277,18 @@ strided_sweep_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const double *ge = lid == lid_c ? s_ge + p * (2 * P) : GE + ((int64_t)lid * P + p) * (2 * P);
     const int64_t sbytes = stride * (int64_t)sizeof(double);
     if (FINAL && live && do_prefetch && (w & 3) == 0) {
-      // warm L2 with the T_in rows this tile adds at the end (one lane per 32-byte sector); addresses by pointer
+      // warm L2 with the first do_prefetch T_in rows of the chunk (one lane per 32-byte sector); addresses by pointer
       // increments: base + q * stride with a 64-bit run-time stride cost ~20 instructions per row
       const char *ti = reinterpret_cast<const char *>(Tin + off);
-      if (full) {
+      const int nq = min(rows, do_prefetch);
+      if (nq == M) {
 #pragma unroll
         for (int q = 0; q < M; ++q) {
           prefetch_l2(ti);
           ti += sbytes;
         }
       } else {
-        for (int q = 0; q < rows; ++q) {
+        for (int q = 0; q < nq; ++q) {
           prefetch_l2(ti);
           ti += sbytes;
         }
@@ -440,9 +441,10 @@ int launch_tma(hs2_plan *pl, const hs2_axis_tables &ax, double *data, const doub
   const bool use_rows = group_stride == 0 && zmode == 3 && !(lines_per_group & 1) && !(stride & 1) &&
                         !(reinterpret_cast<uintptr_t>(data) & 15);
   const uint8_t *ucode = (FINAL && pl->has_utab[axis] && !(pl->d.flags & HS2_FLAG_NO_UTAB)) ? ax.d_ucode : nullptr;
-  // L2 warm-up of the tile's T_in rows at tile start: off since the T_in / store phase addresses its rows by pointer
+  // L2 warm-up of the tile's T_in rows at tile start (HS2_PREFETCH = rows per chunk to warm, 1 = all): off since the T_in / store phase addresses its rows by pointer
   // increments (measured at 512^3: z sweep 0.630 ms with it, 0.571 ms without; 256^3: 0.080 / 0.078)
-  static const int pf = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 0;
+  static const int pf_env = getenv("HS2_PREFETCH") ? atoi(getenv("HS2_PREFETCH")) : 0;
+  const int pf = pf_env == 1 ? M : pf_env;
   static const int pace = getenv("HS2_Z_PACE") ? atoi(getenv("HS2_Z_PACE")) : 1;
   const int BR = L < 256 ? L : 256;
   const int n_boxes = (L + BR - 1) / BR;

@@ -51,3 +51,31 @@ def test_argument_validation_without_gpu():
     assert b"empty grid" in L.hs2_last_error()
     assert L.hs2_tridiag_scratch_bytes(1 << 20) >= (1 << 20) // 2048 * 32
     assert L.hs2_step(None, None, None, None, None, None, None, None) == -1
+    # many-steps / observation entry points (ABI 6): NULL plan or fields are argument errors, not crashes
+    assert L.hs2_run_steps(None, None, None, None, 0, 10, 1, None, 0, None, None, 0.0, None, 1, None) == -1
+    assert b"hs2_run_steps" in L.hs2_last_error()
+    assert L.hs2_observe(None, None, None, 0, None, None, 0.0, None) == -1
+    assert b"hs2_observe" in L.hs2_last_error()
+
+
+def test_source_active_matches_evaluate_sources():
+    """AdiPlan.source_active (time logic only; decides which steps run_adi_steps_n hands to hs2_run_steps) agrees with
+    what evaluate_sources produces, step by step, on the problem that carries all four source kinds."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import heatsim2_b200 as hs
+    import problems
+    from heatsim2_b200.plan import AdiPlan
+    prob = problems.sources_demo(hs)
+    P, S = hs.setup(*prob["setup_args"])
+    plan = P.plan
+    active = []
+    for n in range(12):
+        t = prob["t0"] + n * prob["dt"]
+        table, dense = plan.evaluate_sources(t, prob["dt"], prob["volumetric_elements"], prob["volumetric"])
+        has = table is not None or (dense is not None and np.any(dense))
+        assert AdiPlan.source_active(t, prob["volumetric"]) or not has       # never misses an active source
+        active.append(AdiPlan.source_active(t, prob["volumetric"]))
+    assert active[0] and not any(active[6:])         # the flash at t = 0; everything is over after 0.08 s
+    assert not AdiPlan.source_active(0.5, None) and not AdiPlan.source_active(0.5, ())
