@@ -657,7 +657,8 @@ class AdiPlan(object):
     def source_active(t, volumetric):
         """True when a step taken at time ``t`` may carry a volumetric source (the time conditions of
         ``evaluate_sources`` / alternatingdirection_c_pyx.pyx:301-383, without touching any array)."""
-        from . import NO_SOURCE, STEPPED_SOURCE
+        from . import (NO_SOURCE, STEPPED_SOURCE, IMPULSE_SOURCE, IMPULSE_POINT_SOURCE_JOULES,
+                       SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE)
         for entry in (volumetric if volumetric is not None else ()):
             kind = entry[0]
             if kind == NO_SOURCE:
@@ -665,8 +666,11 @@ class AdiPlan(object):
             if kind == STEPPED_SOURCE:
                 if t >= entry[1] and t <= entry[2]:
                     return True
-            elif t == entry[1]:      # the three impulse kinds fire at exactly t == t_impulse
-                return True
+            elif kind in (IMPULSE_SOURCE, IMPULSE_POINT_SOURCE_JOULES, SPATIALLY_Z_DECAYING_TEMPORAL_IMPULSE):
+                if t == entry[1]:    # the three impulse kinds fire at exactly t == t_impulse
+                    return True
+            else:
+                return True          # unknown kind: let evaluate_sources raise for it
         return False
 
     def evaluate_sources(self, t, dt, volumetric_elements, volumetric):
