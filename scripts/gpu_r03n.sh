@@ -1,0 +1,3 @@
+set -x
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
