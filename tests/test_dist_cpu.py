@@ -83,6 +83,58 @@ def test_slabs_match_oracle(world, name, kwargs):
     assert util.relerr(got, want) <= 1e-12
 
 
+def _worker_n(rank, world, port, name, kwargs, nsteps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import heatsim2_b200 as hs
+        from heatsim2_b200 import dist as hdist
+        prob = problems.ALL[name](hs, **kwargs)
+        P, S = hdist.setup(*prob["setup_args"], plan_class=emul.EmulDistPlan)
+        k0, k1 = P.slab
+        T0 = torch.from_numpy(np.array(prob["T0"][k0:k1]))
+        ve = prob["volumetric_elements"][k0:k1]
+        Tn, rec = hs.run_adi_steps_n(P, S, prob["t0"], prob["dt"], T0, ve, prob["volumetric"], nsteps,
+                                     probes=[(1, 2, 3)], surface_dz=prob["dz"], every=2)
+        q.put((rank, k0, k1, Tn.numpy(), rec))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_run_adi_steps_n_on_slab_plans():
+    """run_adi_steps_n on a multi-rank plan (no native loop there: one library call per step, observation by tensor
+    indexing on the rank's slab): field, probe and surface records against the oracle"""
+    import heatsim2_b200 as hs
+    kwargs, nsteps, world = dict(nz=32, ny=12, nx=14), 6, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_n, args=(r, world, port, "steelonfoam", kwargs, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    prob = problems.steelonfoam(hs, **kwargs)
+    O = adi_oracle.setup(*prob["setup_args"])
+    T, hist = np.array(prob["T0"]), []
+    for it in range(nsteps):
+        T = O.step(prob["t0"] + it * prob["dt"], prob["dt"], T)
+        if (it + 1) % 2 == 0:
+            hist.append(T.copy())
+    scale = np.abs(T).max()
+    assert util.relerr(np.concatenate([p[3] for p in parts], axis=0), T) <= 1e-12
+    for rank, k0, k1, _, rec in parts:
+        assert rec["step"] == [2, 4, 6]
+        want_probe = np.array([h[k0 + 1, 2, 3] for h in hist])
+        assert np.abs(rec["probes"][:, 0] - want_probe).max() <= 1e-12 * scale
+        # the surface estimate reads the slab's own first two planes (the physical z-min surface on rank 0)
+        want_surf = np.array([hs.surface_temperature.insulating_z_min_surface_temperature(h[k0:k1], prob["dz"]) for h in hist])
+        assert np.abs(rec["surface"] - want_surf).max() <= 1e-12 * scale
+
+
 def test_neighbour_exchange_and_pipelining():
     """weakly coupled z-lines (thin plies): the interface band is a few chunks, so
     slabs exchange with their nearest neighbours only, in two pipelined line ranges"""
