@@ -125,7 +125,7 @@ int hs2_run_steps(hs2_plan *plan, double *d_T_a, double *d_T_b, double *d_work, 
   HS2_REQUIRE(!d_surface_rec || (plan->d.nz >= 2 && dz != 0.0), "hs2_run_steps: the surface estimate needs two planes and dz != 0");
   Observer obs{d_probe_cells, n_probes, d_probe_rec, d_surface_rec, plan->d.ny * plan->d.nx, dz,
                reinterpret_cast<unsigned long long *>(d_counter)};
-  HS2_REQUIRE(!obs.active() || d_counter, "hs2_run_steps: recording needs d_counter (one zero-initialised 64-bit word)");
+  HS2_REQUIRE(!obs.active() || d_counter, "hs2_run_steps: recording needs d_counter (a 64-bit device word holding the first free record row)");
   cudaStream_t st = (cudaStream_t)stream;
   double *const buf[2] = {d_T_a, d_T_b};
   // replay unit: a whole number of recording periods that also brings the field back to the buffer it started in
